@@ -1,0 +1,260 @@
+// Tile GEMM on the FP64 tensor-core path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4) for sm_100a.
+//
+//   C(I,J)  =  C(I,J) - sum_k A(I,k) * B(J,k)^T        (SYRK / GEMM trailing updates, triangular-solve updates)
+//   C(I,J)  =           sum_k A(I,k) * B(k,k)^T        (TRSM against an inverted diagonal tile, overwrite)
+//
+// over 128x128 fp64 tiles in the chunked K-major layout of gpx_common.cuh.  Both operands are "row x k" with k
+// fastest, which is exactly what mma.m8n8k4.row.col wants, so the same kernel serves the Cholesky trailing
+// update (A = B = factored panel), the panel TRSM (B = inverted diagonal tile) and the predictive-variance
+// triangular solve (A = transposed cross-kernel workspace, B = L).
+//
+// Structure (one persistent CTA per SM, 288 threads):
+//   * warp 8 lane 0 = producer: for every output tile and every 16-wide K slice issues two 16 KB 1-D TMA bulk
+//     copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) into a 6-stage shared-memory ring, signalled
+//     through mbarriers (full/empty);
+//   * warps 0..7 = consumers, 2 (M) x 4 (N), each owning a 64x32 accumulator block = 8x4 DMMA 8x8 fragments held
+//     in registers (64 doubles / thread).  Per 8-k chunk a warp issues 12 conflict-free LDS.128 and 64 DMMA.
+//   * accumulate mode initialises the accumulators with the old C tile (coalesced 512 B fragment loads issued
+//     while the pipeline fills) and feeds NEGATED A fragments, so the epilogue is store-only.
+//
+// Roofline: FP64 tensor.  Algorithmic flops per output tile = 2 * 128^3 * (k1 - k0); measured DMMA peak on this
+// pool's B200 is 36.96 TFLOP/s (profiles/r01_fp64_peak.txt).
+#include <cstdio>
+#include <cstdlib>
+#include "gpx_common.cuh"
+
+namespace {
+
+constexpr int kStages = 6;
+constexpr int kStageK = 16;                              // k columns per stage
+constexpr int kOperBytes = GPX_TILE * kStageK * 8;       // 16 KB per operand per stage
+constexpr int kStageBytes = 2 * kOperBytes;              // A + B
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStages * 8 + 128;
+#ifndef GPX_WAR_FENCE_MODE
+#define GPX_WAR_FENCE_MODE 1
+#endif
+constexpr int kStrip = 8;                                // output tile columns per rasterisation strip
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// Output-tile enumeration shared by producer and consumers: strips of kStrip tile columns, row-major inside a
+// strip, so the CTAs running together share few operand panels (L2 reuse).  Invalid (above-diagonal) slots of a
+// triangular job are skipped.
+struct TileWalk {
+    int tri, i0, i1, j0, j1;
+    int strip_c0, strip_w, strip_r0;
+    long long strip_begin, strip_end;
+    __device__ void init(const GemmJob& j) {
+        tri = j.tri; i0 = j.i0; i1 = j.i1; j0 = j.j0; j1 = j.j1;
+        strip_c0 = j0;
+        set_strip();
+        strip_begin = 0;
+        strip_end = (long long)(i1 - strip_r0) * strip_w;
+    }
+    __device__ void set_strip() {
+        strip_w = min(kStrip, j1 - strip_c0);
+        strip_r0 = tri ? max(i0, strip_c0) : i0;
+        if (strip_r0 > i1) strip_r0 = i1;
+    }
+    // returns false when t is past the end; sets I,J and valid
+    __device__ bool locate(long long t, int& I, int& J, bool& valid) {
+        while (t >= strip_end) {
+            strip_c0 += strip_w;
+            if (strip_c0 >= j1) return false;
+            set_strip();
+            strip_begin = strip_end;
+            strip_end = strip_begin + (long long)(i1 - strip_r0) * strip_w;
+        }
+        long long u = t - strip_begin;
+        I = strip_r0 + (int)(u / strip_w);
+        J = strip_c0 + (int)(u % strip_w);
+        valid = !tri || I >= J;
+        return true;
+    }
+};
+
+template <bool kOverwrite>
+__global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob job) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    TileWalk walk;
+    walk.init(job);
+    int stage = 0;
+    uint32_t phase = 0;
+    const int nslice = GPX_TILE / kStageK;  // 8 slices per operand tile
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            for (long long t = blockIdx.x;; t += gridDim.x) {
+                int I, J; bool valid;
+                if (!walk.locate(t, I, J, valid)) break;
+                if (!valid) continue;
+                for (int kb = job.k0; kb < job.k1; kb++) {
+                    const double* a = tile_ptr(job.A, I, kb);
+                    const double* b = job.bdiag ? tile_ptr(job.B, kb, kb) : tile_ptr(job.B, J, kb);
+                    for (int s = 0; s < nslice; s++) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], kStageBytes);
+                        unsigned char* dst = smem + stage * kStageBytes;
+                        bulk_g2s(dst, a + s * (GPX_TILE * kStageK), kOperBytes, &full[stage]);
+                        bulk_g2s(dst + kOperBytes, b + s * (GPX_TILE * kStageK), kOperBytes, &full[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------- consumers ----------------
+        const int wm = warp >> 2, wn = warp & 3;
+        const int g = lane >> 2, tq = lane & 3;
+        // fragment offsets inside an 8-k chunk ([row][8] doubles)
+        const int a_off = (wm * 64 + g) * 8 + 2 * tq;
+        const int b_off = (wn * 32 + g) * 8 + 2 * tq;
+        // accumulator fragment (i,j) lives at tile offset  ((wn*32 + j*8) >> 3) * 1024 + (wm*64 + i*8 + g) * 8 + 2*tq
+        const int c_off = (wn * 4) * 1024 + (wm * 64 + g) * 8 + 2 * tq;
+
+        for (long long t = blockIdx.x;; t += gridDim.x) {
+            int I, J; bool valid;
+            if (!walk.locate(t, I, J, valid)) break;
+            if (!valid) continue;
+            double* ctile = tile_ptr(job.C, I, J);
+            double acc[8][4][2];
+            if (kOverwrite) {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        double2 v = __ldcg(reinterpret_cast<const double2*>(ctile + c_off + j * 1024 + i * 64));
+                        acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+                    }
+            }
+            for (int kb = job.k0; kb < job.k1; kb++) {
+                for (int s = 0; s < nslice; s++) {
+                    mbar_wait(&full[stage], phase);
+                    const double* As = reinterpret_cast<const double*>(smem + stage * kStageBytes);
+                    const double* Bs = As + GPX_TILE * kStageK;
+#pragma unroll
+                    for (int ch = 0; ch < kStageK / 8; ch++) {
+                        double2 bf[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            bf[j] = *reinterpret_cast<const double2*>(Bs + ch * 1024 + b_off + j * 64);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            double2 af = *reinterpret_cast<const double2*>(As + ch * 1024 + a_off + i * 64);
+                            if (!kOverwrite) { af.x = -af.x; af.y = -af.y; }
+#pragma unroll
+                            for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af.x, bf[j].x);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af.y, bf[j].y);
+                        }
+                    }
+                    // Cross-proxy WAR: the stage is re-filled by an async-proxy bulk copy as soon as the empty barrier
+                    // completes, while it was read here through the generic proxy (LDS).  Without this proxy fence the
+                    // refill was observed to overtake the reads on B200 (non-deterministic tiles at N >= ~5000;
+                    // tools/gpu_debug2.py), with it 24/24 repeated factorizations are bit-identical.
+#if GPX_WAR_FENCE_MODE == 1
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+#else
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive(&empty[stage]);
+                    }
+#endif
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    *reinterpret_cast<double2*>(ctile + c_off + j * 1024 + i * 64) =
+                        make_double2(acc[i][j][0], acc[i][j][1]);
+            gpx_publish_for_async_proxy();
+        }
+    }
+}
+
+long long count_slots(const GemmJob& j) {
+    long long total = 0;
+    for (int c0 = j.j0; c0 < j.j1; c0 += kStrip) {
+        int w = (j.j1 - c0 < kStrip) ? (j.j1 - c0) : kStrip;
+        int r0 = j.tri ? (j.i0 > c0 ? j.i0 : c0) : j.i0;
+        if (r0 > j.i1) r0 = j.i1;
+        total += (long long)(j.i1 - r0) * w;
+    }
+    return total;
+}
+
+}  // namespace
+
+void gpx_gemm_init() {
+    cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+}
+
+void gpx_launch_gemm(const GemmJob& job, int num_sms, cudaStream_t st, int64_t* launch_counter) {
+    if (job.i1 <= job.i0 || job.j1 <= job.j0 || job.k1 <= job.k0) return;
+    long long slots = count_slots(job);
+    if (slots <= 0) return;
+    int grid = (int)(slots < num_sms ? slots : num_sms);
+    if (job.overwrite)
+        gemm_dmma_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(job);
+    else
+        gemm_dmma_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(job);
+    if (launch_counter) (*launch_counter)++;
+}

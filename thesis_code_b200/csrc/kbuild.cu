@@ -1,0 +1,258 @@
+// Kernel-matrix builders: pairwise stationary kernels (RBF / Matern-5/2 / Matern-3/2 / Exponential, isotropic or
+// ARD) from a Gram product plus a fused distance -> exp/Matern epilogue, written straight into 128x128 tiles of
+// the factor storage (K(X,X) + diag_add*I, lower triangle only) or of the transposed cross-kernel workspace
+// (K(X*,X), fused with the predictive-mean GEMV partial sums).
+//
+// Arithmetic follows GPy's Stationary._unscaled_dist / _scaled_dist (the library the reference's
+// src/kernels.py:4-7 aliases): inputs divided by the lengthscale(s), r^2 = |a|^2 + |b|^2 - 2 a.b clipped at 0,
+// exact 0 on the diagonal of K(X,X), r = sqrt(r^2), then K_of_r.
+//
+// Roofline: the K(X,X) build writes 8 B per element once (HBM-write bound: 8*N(N+1)/2 + 8*N*d bytes) but at small
+// d it is bound by the fp64 exp/sqrt ALU work (~60 DFMA-equivalents per element); both rates are reported.
+#include "gpx_common.cuh"
+
+namespace {
+
+constexpr int kMaxD = 64;
+
+__global__ void scale_x_kernel(const double* __restrict__ X, int64_t N, int64_t Np, int d,
+                               const double* __restrict__ ls, int n_ls, double* __restrict__ Xs,
+                               double* __restrict__ xsq) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    double s = 0.0;
+    for (int k = 0; k < d; k++) {
+        double v = 0.0;
+        if (i < N) v = X[i * d + k] / ls[n_ls == 1 ? 0 : k];
+        Xs[i * d + k] = v;
+        s += v * v;
+    }
+    xsq[i] = s;
+}
+
+// One CTA (256 threads) per output tile.  Rows come from (Xa, asq) tile ti, columns from (Xb, bsq) tile tj.
+// Thread mapping = the DMMA accumulator fragment pattern: lane (g = lane>>2, t = lane&3) of warp w owns, for each
+// of its 2 row blocks and 16 column chunks, the pair (r, c..c+1) -> one 16 B store; a warp stores 512 contiguous B.
+template <bool kSymmetric>
+__device__ __forceinline__ void build_tile(double* __restrict__ out, const double* __restrict__ Xa,
+                                           const double* __restrict__ asq, int64_t Na, int ti,
+                                           const double* __restrict__ Xb, const double* __restrict__ bsq,
+                                           int64_t Nb, int tj, int d, int kernel_id, double variance,
+                                           double diag_add, double* sm, double (*vals)[16][2]) {
+    const int dp = d | 1;
+    double* sa = sm;                      // [128][dp]
+    double* sb = sa + GPX_TILE * dp;      // [128][dp]
+    double* sasq = sb + GPX_TILE * dp;    // [128]
+    double* sbsq = sasq + GPX_TILE;       // [128]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < GPX_TILE * d; e += blockDim.x) {
+        int rr = e / d, k = e - rr * d;
+        sa[rr * dp + k] = Xa[((int64_t)ti * GPX_TILE + rr) * d + k];
+        sb[rr * dp + k] = Xb[((int64_t)tj * GPX_TILE + rr) * d + k];
+    }
+    if (tid < GPX_TILE) {
+        sasq[tid] = asq[(int64_t)ti * GPX_TILE + tid];
+        sbsq[tid] = bsq[(int64_t)tj * GPX_TILE + tid];
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int rb = 0; rb < 2; rb++) {
+        const int r = warp * 16 + rb * 8 + g;
+        const int64_t gi = (int64_t)ti * GPX_TILE + r;
+        double dot[16][2];
+#pragma unroll
+        for (int kc = 0; kc < 16; kc++) { dot[kc][0] = 0.0; dot[kc][1] = 0.0; }
+        for (int k = 0; k < d; k++) {
+            double a = sa[r * dp + k];
+#pragma unroll
+            for (int kc = 0; kc < 16; kc++) {
+                int c = kc * 8 + 2 * t;
+                dot[kc][0] = fma(a, sb[c * dp + k], dot[kc][0]);
+                dot[kc][1] = fma(a, sb[(c + 1) * dp + k], dot[kc][1]);
+            }
+        }
+        const double ra = sasq[r];
+#pragma unroll
+        for (int kc = 0; kc < 16; kc++) {
+            double v[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int c = kc * 8 + 2 * t + h;
+                int64_t gj = (int64_t)tj * GPX_TILE + c;
+                double r2 = -2.0 * dot[kc][h] + (ra + sbsq[c]);
+                r2 = fmax(r2, 0.0);
+                double kv;
+                if (kSymmetric) {
+                    if (gi == gj) r2 = 0.0;
+                    kv = gpx_k_of_r2(kernel_id, variance, r2);
+                    if (gi == gj) kv += diag_add;
+                    if (gi >= Na || gj >= Nb) kv = (gi == gj) ? 1.0 : 0.0;  // identity padding
+                } else {
+                    kv = gpx_k_of_r2(kernel_id, variance, r2);
+                    if (gi >= Na || gj >= Nb) kv = 0.0;
+                }
+                v[h] = kv;
+            }
+            if (vals) { vals[rb][kc][0] = v[0]; vals[rb][kc][1] = v[1]; }
+            if (out) *reinterpret_cast<double2*>(out + kc * 1024 + r * 8 + 2 * t) = make_double2(v[0], v[1]);
+        }
+    }
+    if (out) gpx_publish_for_async_proxy();
+}
+
+// K(X,X) + diag_add I into the packed lower factor storage: grid (nt, number of tile columns handled here).
+__global__ void __launch_bounds__(256) kbuild_lower_kernel(TileMat L, int nt, int jfirst, int jstep,
+                                                           const double* __restrict__ Xs,
+                                                           const double* __restrict__ xsq, int64_t N, int d,
+                                                           int kernel_id, double variance, double diag_add) {
+    extern __shared__ __align__(16) double sm[];
+    const int J = jfirst + blockIdx.y * jstep;
+    const int I = blockIdx.x;
+    if (J >= nt || I < J) return;
+    build_tile<true>(tile_ptr(L, I, J), Xs, xsq, N, I, Xs, xsq, N, J, d, kernel_id, variance, diag_add, sm, nullptr);
+}
+
+// K(X*, X) tiles (rows = test points, cols = training points) into Tt (if Tt.base != null) and the fused
+// predictive-mean partial sums  mean_partial[J][n][o] = sum_{j in tile J} K(x*_n, x_j) alpha[o][j].
+// grid (nbt, nt).
+__global__ void __launch_bounds__(256) kcross_kernel(TileMat Tt, int nbt, int nt, const double* __restrict__ Xt,
+                                                     const double* __restrict__ xtsq, int64_t Nt_valid,
+                                                     const double* __restrict__ Xs, const double* __restrict__ xsq,
+                                                     int64_t N, int d, int kernel_id, double variance,
+                                                     const double* __restrict__ alpha, int O, int64_t Np,
+                                                     double* __restrict__ mean_partial) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[4][GPX_TILE];  // [t][row]
+    const int n = blockIdx.x, J = blockIdx.y;
+    double vals[2][16][2];
+    double* out = Tt.base ? tile_ptr(Tt, n, J) : nullptr;
+    build_tile<false>(out, Xt, xtsq, Nt_valid, n, Xs, xsq, N, J, d, kernel_id, variance, 0.0, sm, vals);
+    if (!mean_partial) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    for (int o = 0; o < O; o++) {
+        const double* al = alpha + (int64_t)o * Np + (int64_t)J * GPX_TILE;
+#pragma unroll
+        for (int rb = 0; rb < 2; rb++) {
+            double s = 0.0;
+#pragma unroll
+            for (int kc = 0; kc < 16; kc++) {
+                int c = kc * 8 + 2 * t;
+                s = fma(vals[rb][kc][0], al[c], s);
+                s = fma(vals[rb][kc][1], al[c + 1], s);
+            }
+            red[t][warp * 16 + rb * 8 + g] = s;
+        }
+        __syncthreads();
+        if (tid < GPX_TILE) {
+            double s = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+            mean_partial[((int64_t)J * nbt + n) * GPX_TILE * O + (int64_t)tid * O + o] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// mean[n*128 + r][o] = mean_const + sum_J mean_partial[J][n][r][o]   (fixed summation order: deterministic)
+__global__ void mean_reduce_kernel(const double* __restrict__ mean_partial, int nbt, int nt, int O, double mean_const,
+                                   double* __restrict__ mean, int64_t row0, int64_t Ns) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index over nbt*128*O
+    int64_t total = (int64_t)nbt * GPX_TILE * O;
+    if (e >= total) return;
+    double s = 0.0;
+    for (int J = 0; J < nt; J++) s += mean_partial[(int64_t)J * total + e];
+    int64_t row = row0 + e / O;
+    if (row < Ns) mean[row * O + (e % O)] = s + mean_const;
+}
+
+// var[n] = variance + noise - sum_j Tt[n][j]^2 : one CTA per test tile, 256 threads = (row, half of the chunks)
+__global__ void __launch_bounds__(256) var_reduce_kernel(TileMat Tt, int nt, double prior_var, double* __restrict__ var,
+                                                         int64_t row0, int64_t Ns) {
+    __shared__ double red[GPX_TILE];
+    const int n = blockIdx.x, tid = threadIdx.x, r = tid & 127, half = tid >> 7;
+    double s0 = 0.0, s1 = 0.0;
+    for (int J = 0; J < nt; J++) {
+        const double* tp = tile_ptr(Tt, n, J);
+#pragma unroll
+        for (int kc = 0; kc < 8; kc++) {
+            const double2* p = reinterpret_cast<const double2*>(tp + (half * 8 + kc) * 1024 + r * 8);
+            double2 a = p[0], b = p[1], c = p[2], e = p[3];
+            s0 = fma(a.x, a.x, s0); s1 = fma(a.y, a.y, s1);
+            s0 = fma(b.x, b.x, s0); s1 = fma(b.y, b.y, s1);
+            s0 = fma(c.x, c.x, s0); s1 = fma(c.y, c.y, s1);
+            s0 = fma(e.x, e.x, s0); s1 = fma(e.y, e.y, s1);
+        }
+    }
+    double s = s0 + s1;
+    if (half == 1) red[r] = s;
+    __syncthreads();
+    if (half == 0) {
+        s += red[r];
+        int64_t row = row0 + (int64_t)n * GPX_TILE + r;
+        if (row < Ns) var[row] = prior_var - s;
+    }
+}
+
+// dense row-major view of a tiled matrix (tests / export / small full covariance)
+__global__ void detile_kernel(TileMat M, int lower, int64_t rows, int64_t cols, double* __restrict__ out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r = blockIdx.y;
+    if (c >= cols || r >= rows) return;
+    double v = 0.0;
+    if (!lower || r >= c) v = tile_ptr(M, (int)(r >> 7), (int)(c >> 7))[gpx_tile_idx((int)(r & 127), (int)(c & 127))];
+    out[r * cols + c] = v;
+}
+
+}  // namespace
+
+static size_t kb_smem(int d) { return (size_t)(2 * GPX_TILE * (d | 1) + 2 * GPX_TILE) * sizeof(double); }
+
+int gpx_kbuild_max_d() { return kMaxD; }
+
+void gpx_kbuild_init() {
+    size_t s = kb_smem(kMaxD);
+    cudaFuncSetAttribute(kbuild_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s);
+    cudaFuncSetAttribute(kcross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s);
+}
+
+void gpx_launch_scale_x(const double* X, int64_t N, int64_t Np, int d, const double* ls, int n_ls, double* Xs,
+                        double* xsq, cudaStream_t st) {
+    int threads = 256;
+    int blocks = (int)((Np + threads - 1) / threads);
+    scale_x_kernel<<<blocks, threads, 0, st>>>(X, N, Np, d, ls, n_ls, Xs, xsq);
+}
+
+void gpx_launch_kbuild_lower(TileMat L, int nt, int jfirst, int jstep, int ncols, const double* Xs,
+                             const double* xsq, int64_t N, int d, int kernel_id, double variance, double diag_add,
+                             cudaStream_t st) {
+    if (ncols <= 0) return;
+    dim3 grid(nt, ncols);
+    kbuild_lower_kernel<<<grid, 256, kb_smem(d), st>>>(L, nt, jfirst, jstep, Xs, xsq, N, d, kernel_id, variance,
+                                                       diag_add);
+}
+
+void gpx_launch_kcross(TileMat Tt, int nb, int nbt_layout, int nt, const double* Xt, const double* xtsq,
+                       int64_t Nt_valid, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
+                       double variance, const double* alpha, int O, int64_t Np, double* mean_partial, cudaStream_t st) {
+    dim3 grid(nb, nt);
+    kcross_kernel<<<grid, 256, kb_smem(d), st>>>(Tt, nbt_layout, nt, Xt, xtsq, Nt_valid, Xs, xsq, N, d, kernel_id, variance,
+                                                 alpha, O, Np, mean_partial);
+}
+
+void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, double mean_const, double* mean,
+                            int64_t row0, int64_t Ns, cudaStream_t st) {
+    // nbt = layout stride (test tiles per tile column of mean_partial); rows past Ns are skipped in the kernel
+    int64_t total = (int64_t)nbt * GPX_TILE * O;
+    int threads = 128;
+    mean_reduce_kernel<<<(int)((total + threads - 1) / threads), threads, 0, st>>>(mean_partial, nbt, nt, O,
+                                                                                  mean_const, mean, row0, Ns);
+}
+
+void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, double prior_var, double* var, int64_t row0, int64_t Ns,
+                           cudaStream_t st) {
+    var_reduce_kernel<<<nbt, 256, 0, st>>>(Tt, nt, prior_var, var, row0, Ns);
+}
+
+void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double* out, cudaStream_t st) {
+    dim3 grid((unsigned)((cols + 255) / 256), (unsigned)rows);
+    detile_kernel<<<grid, 256, 0, st>>>(M, lower, rows, cols, out);
+}
