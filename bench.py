@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the exact-GP hot path (fit + predict) -- the driver's contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C1..C5] [--N n --Ns m]
+
+A "step" = one full pass of the hot path over one synthetic data set: K-build + Cholesky + alpha + LML (fit) and
+predictive mean + variance for every test point (predict).  Workloads are the BASELINE.json configs
+(thesis_code_b200/synthetic.py).  N=1 runs C4 (N=60000, d=1, N*=100000), the largest configuration that BASELINE
+lists for a single B200; N>1 runs C5 (N=200000, d=8, N*=2500) block-column-cyclically sharded over the ranks.
+
+value        = algorithmic fp64 TFLOP/s of fit+predict (N^3/3 + N^2 N* flop / step time), inputs resident in HBM.
+e2e          = the same through the public GPModel API with HOST numpy buffers (H2D / D2H copies inside the timing).
+roofline     = the dominant kernel (DMMA tile GEMM, csrc/gemm_dmma.cu): algorithmic flops of the two tensor phases
+               / summed CUDA-event time of its launches, against the measured FP64 DMMA peak of this pool's B200.
+cpu_baseline = the numpy/scipy oracle (a port of the reference's GPy path) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_DMMA_PEAK_TFLOPS = 36.96   # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.txt)
+METRIC = "exact-GP fit+predict FP64 throughput (algorithmic N^3/3 + N^2*N* flop per fit+predict)"
+
+
+def algorithmic_flops(N, Ns):
+    return float(N) ** 3 / 3.0 + float(N) ** 2 * float(Ns)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def kernel_args(cfg):
+    from thesis_code_b200 import _gpx
+    kw = cfg["model"]["kwargs"]
+    kk = kw["kernel"]["kwargs"]
+    ls = np.atleast_1d(np.asarray(kk.get("lengthscale", 1.0), dtype=np.float64))
+    if kk.get("ARD", False) and ls.size == 1:
+        ls = np.full(cfg["d"], ls[0])
+    return _gpx.KERNEL_IDS[kw["kernel"]["name"]], float(kk.get("variance", 1.0)), ls, float(kw["noise_prior"])
+
+
+def cpu_oracle_step(cfg):
+    """One fit+predict of the oracle on the host; returns seconds."""
+    from oracle import gp_oracle as o
+    kw = cfg["model"]["kwargs"]
+    t0 = time.perf_counter()
+    m = o.OracleGPModel(kernel=kw["kernel"], noise_prior=kw["noise_prior"])
+    m.init(cfg["X"], cfg["Y"])
+    m.get_statistics(cfg["Xs"], full_cov=False)
+    return time.perf_counter() - t0
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count() or 1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, workload, rank):
+    """--impl reference: the reference's CPU implementation of the path.  GPy (where the reference's arithmetic lives)
+    is not installable here, so this times the oracle port with all host BLAS threads on a bounded sample."""
+    if rank != 0:
+        return
+    from thesis_code_b200 import synthetic
+    sN, sNs = (args.N or 12000), (args.Ns or 2000)
+    cfg = synthetic.make_config(workload, N=sN, Ns=sNs)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_oracle_step(cfg)
+    times = [cpu_oracle_step(cfg) for _ in range(args.steps)]
+    t = float(np.mean(times))
+    val = algorithmic_flops(cfg["N"], cfg["Ns"]) / t / 1e12
+    sample = "%s generator at N=%d, N*=%d (bounded sample; full size is N=%s)" % (workload, cfg["N"], cfg["Ns"], {"C4": "60000", "C5": "200000"}.get(workload, "?"))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload + " (bounded CPU sample)", "N": cfg["N"], "d": cfg["d"], "N_test": cfg["Ns"]},
+            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--N", type=int, default=None)
+    ap.add_argument("--Ns", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = args.workload or ("C4" if args.gpus == 1 else "C5")
+
+    if args.impl == "reference":
+        run_reference(args, workload, rank)
+        return
+
+    import torch
+    from thesis_code_b200 import GPModel, _gpx, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the exact-GP path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = synthetic.make_config(workload, N=args.N, Ns=args.Ns)
+    N, d, Ns = cfg["N"], cfg["d"], cfg["Ns"]
+    kid, variance, ls, noise = kernel_args(cfg)
+    flops = algorithmic_flops(N, Ns)
+
+    h = _gpx.Handle(local_rank)
+    if world > 1:
+        from thesis_code_b200 import distributed as gdist
+        gdist.init_handle_comm(h, dist, rank, world)
+    h.set_option("gemm_timing", 1)
+    ext = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))
+
+    # inputs resident in HBM for `value`
+    dX = torch.from_numpy(cfg["X"]).cuda()
+    dY = torch.from_numpy(cfg["Y"]).cuda()
+    dXs = torch.from_numpy(cfg["Xs"]).cuda()
+    dmean = torch.empty((Ns, 1), dtype=torch.float64, device="cuda")
+    dvar = torch.empty((Ns,), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+
+    def device_step():
+        h.fit_device(dX.data_ptr(), N, d, dY.data_ptr(), 1, kid, variance, ls, noise)
+        h.predict_device(dXs.data_ptr(), Ns, dmean.data_ptr(), dvar.data_ptr(), True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    h.gemm_stats()
+    launches0 = h.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase_acc = {}
+    e0.record(ext)
+    for _ in range(args.steps):
+        device_step()
+        for k, v in h.phase_ms().items():
+            phase_acc[k] = phase_acc.get(k, 0.0) + v
+    e1.record(ext)
+    barrier()
+    sampler.stop_flag = True
+    ms_total = e0.elapsed_time(e1)
+    gemm_ms, gemm_issued, gemm_launches = h.gemm_stats()
+    launches = h.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = flops / (ms_step * 1e-3) / 1e12
+    phases = {k: v / args.steps for k, v in phase_acc.items()}
+
+    # ---- e2e: the public GPModel API with host numpy buffers (H2D + D2H inside the timed region) ----------------
+    model = GPModel.from_config(cfg["model"]["kwargs"])
+    model.device = local_rank
+    model._handle = h
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        model.init(cfg["X"], cfg["Y"])
+        mean, var = model.get_statistics(cfg["Xs"], full_cov=False)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h.gemm_stats()
+    e2e_val = flops / (e2e_ms * 1e-3) / 1e12
+    h2d = int(cfg["X"].nbytes + cfg["Y"].nbytes + cfg["Xs"].nbytes)
+    d2h = int(mean.nbytes // 1 + Ns * 8)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+    tensor_flops_per_step = flops * args.steps           # N^3/3 (Cholesky) + N^2 N* (variance solve): both run in the tile GEMM
+    achieved = tensor_flops_per_step / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    chol_tflops = (float(N) ** 3 / 3) / (phases["cholesky"] * 1e-3) / 1e12
+    trsm_tflops = (float(N) ** 2 * Ns) / (phases["predict_trsm"] * 1e-3) / 1e12 if phases.get("predict_trsm", 0) > 0 else None
+    peaks = measured_peaks()
+    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA tile GEMM)", "achieved": achieved,
+                "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": (achieved / FP64_DMMA_PEAK_TFLOPS) if achieved else None,
+                "traffic": None,
+                "peak_source": "fallback: MEASURED_PEAKS.json has no FP64 figure; 36.96 TFLOP/s = register-resident "
+                               "mma.sync.m8n8k4.f64 loop measured on this pool's B200 (profiles/r01_fp64_peak.txt)",
+                "gemm_launches": gemm_launches, "gemm_ms_per_step": gemm_ms / args.steps,
+                "issued_tflops": gemm_issued / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+                "kernel_share_of_step": gemm_ms / ms_total if ms_total > 0 else None}
+
+    # ---- CPU baseline: oracle port on a bounded sample ------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        sN, sNs = min(N, 12000), min(Ns, 2000)
+        scfg = synthetic.make_config(workload, N=sN, Ns=sNs)
+        t = cpu_oracle_step(scfg)
+        cpu = {"value": algorithmic_flops(sN, sNs) / t / 1e12, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
+               "sample": "oracle (numpy/scipy port of the GPy path) on the %s generator at N=%d, N*=%d: %.1f s" % (workload, sN, sNs, t)}
+
+    line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (workload, {"C4": "1-D natural-sound-shaped exact GP, N=60k, 100k test points",
+                                                           "C5": "ARD-RBF exact GP d=8, N=200k, block-cyclic Cholesky",
+                                                           "C3": "Matern-5/2 ARD kin40k-shaped d=8, N=40k",
+                                                           "C2": "ARD-RBF Genz oscillatory d=10, N=20k",
+                                                           "C1": "RBF Sinc 1-D, N=1000"}[workload]),
+                       "N": N, "d": d, "N_test": Ns, "kernel": cfg["model"]["kwargs"]["kernel"]["name"],
+                       "parallelism": "1 GPU" if world == 1 else "block-column-cyclic x%d" % world,
+                       "l2_policy": "inputs larger than L2 (factor %.1f GB >> 126 MB)" % (N * (N + 128) / 2 * 8 / 1e9)},
+            "fit_predict_sec": ms_step * 1e-3, "cholesky_tflops": chol_tflops,
+            "cholesky_frac_of_fp64_peak": chol_tflops / FP64_DMMA_PEAK_TFLOPS / max(world, 1),
+            "variance_trsm_tflops": trsm_tflops, "phase_ms": phases,
+            "hbm_peak_gbs": peaks.get("hbm_gbs"),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "api": "GPModel.init(X, Y) + get_statistics(Xtest, full_cov=False) on numpy arrays"},
+            "gpu_launches": launches, "clocks": sampler.summary()}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

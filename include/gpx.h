@@ -103,8 +103,16 @@ GPX_API double gpx_phase_ms(const gpx_t* h, int phase);
 /* Kernel launches issued by this handle since creation (the `gpu_launches` claim in bench.py). */
 GPX_API int64_t gpx_launch_count(const gpx_t* h);
 /* Tuning knobs (tests exercise several): "outer_tiles" (tile columns per outer Cholesky panel),
- * "predict_batch_tiles" (test tiles per variance batch), "sync_phases" (1: bracket phases with events). */
+ * "predict_batch_tiles" (test tiles per variance batch), "sync_phases" (1: bracket phases with events),
+ * "gemm_timing" (1: per-launch events on the tile-GEMM kernel, see gpx_gemm_stats). */
 GPX_API int gpx_set_option(gpx_t* h, const char* name, int64_t value);
+/* The CUDA stream (cudaStream_t, returned as void*) every kernel of this handle is launched on, so that a caller can
+ * bracket calls with its own CUDA events (bench.py does, via torch.cuda.ExternalStream). */
+GPX_API void* gpx_stream(const gpx_t* h);
+/* With option "gemm_timing"=1 every launch of the DMMA tile-GEMM kernel is bracketed by CUDA events; this returns
+ * (and resets) the accumulated device time in ms, the fp64 flops those launches issued (2*128^3 per tile-k step)
+ * and their count.  Used for the roofline of the dominant kernel. */
+GPX_API int gpx_gemm_stats(gpx_t* h, double* total_ms, double* issued_flops, int64_t* launches);
 /* Device-memory footprint in bytes of the current fit (factor + workspaces). */
 GPX_API int64_t gpx_bytes_allocated(const gpx_t* h);
 

@@ -1,0 +1,112 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/gpx.h declares, the host-side model API
+mirrors the reference's GPModel contract, and nothing silently falls back to the CPU."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+import thesis_code_b200 as pkg
+from thesis_code_b200 import _gpx, kernels, synthetic
+from thesis_code_b200.config_helpers import LazyConstructor, construct_from_module, lazy_construct_from_module
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gpx.h")).read()
+    return sorted(set(re.findall(r"GPX_API[^;(]*?\b(gpx_\w+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    lib = ctypes.CDLL(_gpx.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), "libgpx.so does not export " + s
+    assert sorted(_gpx.SIGNATURES) == syms, "ctypes prototypes out of sync with include/gpx.h"
+    assert _gpx.load_library().gpx_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(_gpx.GpxError):
+        _gpx.Handle(0)
+    m = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "noise_prior": 0.1})
+    with pytest.raises(_gpx.GpxError):
+        m.init(np.zeros((4, 1)), np.zeros((4, 1)))
+
+
+def test_product_path_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "thesis_code_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "gp_oracle" not in src, f
+
+
+def test_config_helpers_semantics():
+    lazy = lazy_construct_from_module(kernels, {"name": "GPyMatern52", "kwargs": {"lengthscale": 0.6, "ARD": True}})
+    assert isinstance(lazy, LazyConstructor)
+    k = lazy(5)
+    assert k.name == "GPyMatern52" and k.input_dim == 5 and k.ARD
+    np.testing.assert_array_equal(k.lengthscale, np.full(5, 0.6))   # scalar broadcast under ARD
+    np.testing.assert_array_equal(k.variance, [1.0])
+    assert lazy_construct_from_module(kernels, None) is None
+    k2 = lazy(3, variance=2.0)                                        # call-site kwargs win
+    assert k2.variance[0] == 2.0
+    m = construct_from_module(pkg, {"name": "GPModel", "kwargs": {"kernel": {"name": "GPyRBF"}, "noise_prior": 0.5}})
+    assert isinstance(m, pkg.GPModel) and m.noise_prior == 0.5 and repr(m) == "ExactGP"
+    assert construct_from_module(pkg, None) is None
+
+
+def test_kernel_spec_validation():
+    assert kernels.GPyRBF(3).lengthscale.shape == (1,)
+    assert kernels.GPyRBF(3, ARD=True).lengthscale.shape == (3,)
+    with pytest.raises(AssertionError):
+        kernels.GPyRBF(3, lengthscale=[1.0, 2.0])            # non-ARD takes one lengthscale
+    with pytest.raises(AssertionError):
+        kernels.GPyRBF(3, lengthscale=[1.0, 2.0], ARD=True)  # wrong count
+    assert {k: v for k, v in _gpx.KERNEL_IDS.items()} == {"GPyRBF": 0, "GPyMatern52": 1, "GPyMatern32": 2, "GPyExponential": 3}
+
+
+def test_gpmodel_contract_without_gpu():
+    m = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF", "kwargs": {"lengthscale": 1.0}}, "noise_prior": 0})
+    # ctor kwargs / defaults of the reference (core_models.py:139-148)
+    for attr, val in dict(do_optimize=False, num_mcmc=0, n_burnin=100, subsample_interval=10, step_size=1e-1,
+                          leapfrog_steps=20, mean_prior=None).items():
+        assert getattr(m, attr) == val
+    assert m.X is None and m.Y is None
+    with pytest.raises(AssertionError):
+        m.add_observations(np.zeros((1, 1)), np.zeros((1, 1)))        # "Call init first"
+    with pytest.raises(AssertionError):
+        m._fit(np.zeros((3, 1)), np.zeros((2, 1)))                     # X/Y size mismatch
+    mo = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True})
+    with pytest.raises(NotImplementedError):
+        mo._fit(np.zeros((3, 1)), np.zeros((3, 1)))
+    # pickling never carries device state
+    m2 = pickle.loads(pickle.dumps(m))
+    assert repr(m2) == "ExactGP" and m2._handle is None
+    assert issubclass(pkg.DerivativeGPModel, pkg.GPModel)
+
+
+def test_synthetic_configs_shapes_and_determinism():
+    sizes = {"C1": (1000, 1, 1000), "C2": (20000, 10, 2500), "C3": (40000, 8, 4000), "C4": (60000, 1, 100000), "C5": (200000, 8, 2500)}
+    for name in ["C1", "C2"]:
+        c = synthetic.make_config(name)
+        assert (c["N"], c["d"], c["Ns"]) == sizes[name]
+        assert c["X"].dtype == np.float64 and c["X"].flags.c_contiguous and c["Y"].shape == (c["N"], 1)
+        c2 = synthetic.make_config(name)
+        assert np.array_equal(c["X"], c2["X"]) and np.array_equal(c["Y"], c2["Y"]) and np.array_equal(c["Xs"], c2["Xs"])
+    for name in ["C3", "C4", "C5"]:
+        c = synthetic.make_config(name, N=500, Ns=64)
+        assert c["X"].shape == (500, sizes[name][1]) and c["Xs"].shape == (64, sizes[name][1])
+        assert c["model"]["name"] == "GPModel" and c["model"]["kwargs"]["do_optimize"] is False
+    c = synthetic.make_config("C1")
+    np.testing.assert_allclose(c["Y"], np.sin(c["X"]) / c["X"])          # Sinc (smooth.py:14-21)
+    assert c["X"].min() >= -20 and c["X"].max() <= 20

@@ -1,0 +1,114 @@
+"""CPU tests of the oracle (oracle/gp_oracle.py): golden vectors, closed forms, kernel identities.
+The reference has no numerical test of GPModel, so these are the known-answer tests SURVEY.md section 8(c) asks for."""
+import numpy as np
+import pytest
+
+from conftest import normwise
+from oracle import gp_oracle as o
+
+TOL = 1e-8  # north_star: 1e-8 relative (normwise) in fp64
+
+
+def test_golden_vectors_pin_the_oracle(golden_cases):
+    assert len(golden_cases) == 16
+    for c in golden_cases:
+        st = o.fit(c["X"], c["Y"], c["kernel"], c["variance"], c["lengthscale"], c["ARD"], c["noise"])
+        mean, var = o.predict(st, c["Xs"], include_noise=True)
+        assert normwise(mean, c["mean"]) < TOL
+        assert normwise(var[:, 0], c["var_with_noise"]) < TOL
+        assert abs(st["lml"] - c["lml"]) / abs(c["lml"]) < TOL
+        mean2, cov = o.predict(st, c["Xs"], full_cov=True, include_noise=True)
+        assert normwise(cov, c["cov_with_noise"]) < TOL
+        assert normwise(mean2, c["mean"]) < TOL
+
+
+def test_closed_form_n1():
+    # N=1: mean = v k/(v+s+j) y ; var = v - v^2 k^2/(v+s+j) + s ; LML = -0.5 log 2pi - 0.5 log(v+s+j) - 0.5 y^2/(v+s+j)
+    v, ls, s, j = 1.7, 0.8, 0.05, 1e-8
+    X = np.array([[0.3]]); Y = np.array([[1.2]]); Xs = np.array([[0.9], [0.3], [5.0]])
+    st = o.fit(X, Y, "GPyRBF", v, ls, False, s)
+    mean, var = o.predict(st, Xs)
+    k = np.exp(-0.5 * ((Xs[:, 0] - 0.3) / ls) ** 2)
+    den = v + s + j
+    np.testing.assert_allclose(mean[:, 0], v * k / den * 1.2, rtol=1e-13)
+    np.testing.assert_allclose(var[:, 0], v - (v * k) ** 2 / den + s, rtol=1e-13)
+    np.testing.assert_allclose(st["lml"], -0.5 * np.log(2 * np.pi) - 0.5 * np.log(den) - 0.5 * 1.2 ** 2 / den, rtol=1e-13)
+
+
+def test_closed_form_n2():
+    v, ls, s = 1.0, 1.0, 0.1
+    X = np.array([[0.0], [1.0]]); Y = np.array([[1.0], [-0.5]])
+    st = o.fit(X, Y, "GPyMatern32", v, ls, False, s)
+    r = 1.0
+    k01 = (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r)
+    a = v + s + 1e-8
+    K = np.array([[a, k01], [k01, a]])
+    alpha = np.linalg.solve(K, Y)
+    np.testing.assert_allclose(st["alpha"], alpha, rtol=1e-12)
+    lml = -0.5 * 2 * np.log(2 * np.pi) - 0.5 * np.log(a * a - k01 * k01) - 0.5 * float((Y.T @ alpha)[0, 0])
+    np.testing.assert_allclose(st["lml"], lml, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", o.KERNEL_NAMES)
+def test_kernel_identities(name):
+    rng = np.random.RandomState(0)
+    X = rng.randn(50, 4)
+    ls = np.array([0.5, 1.0, 2.0, 0.7])
+    K = o.kernel_matrix(name, X, None, 2.5, ls, True)
+    assert np.array_equal(K, K.T) or np.allclose(K, K.T, rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(np.diag(K), 2.5)          # exact sigma_f^2 diagonal (r forced to 0)
+    assert np.linalg.eigvalsh(K + 1e-10 * np.eye(50)).min() > -1e-10
+    # ARD == isotropic(1) on rescaled inputs
+    K2 = o.kernel_matrix(name, X / ls, None, 2.5, 1.0, False)
+    np.testing.assert_allclose(K, K2, rtol=1e-12, atol=1e-15)
+    # cross kernel agrees with the symmetric one off the diagonal
+    Kc = o.kernel_matrix(name, X, X[:7], 2.5, ls, True)
+    off = ~np.eye(50, 7, dtype=bool)
+    np.testing.assert_allclose(Kc[off], K[:, :7][off], rtol=1e-10, atol=1e-14)
+
+
+def test_kernel_smoothness_ordering():
+    # at a fixed moderate distance the smoother kernel is larger: RBF > Matern52 > Matern32 > Exponential
+    r = np.array([[0.0], [0.7]])
+    vals = [o.kernel_matrix(n, r, None, 1.0, 1.0, False)[0, 1] for n in ("GPyRBF", "GPyMatern52", "GPyMatern32", "GPyExponential")]
+    assert vals[0] > vals[1] > vals[2] > vals[3]
+
+
+def test_woodbury_form_matches_trsm_form():
+    rng = np.random.RandomState(3)
+    X = rng.rand(200, 3); Y = rng.randn(200, 1); Xs = rng.rand(40, 3)
+    st = o.fit(X, Y, "GPyMatern52", 1.3, [0.3, 0.5, 0.9], True, 1e-2)
+    m1, v1 = o.predict(st, Xs)
+    m2, v2 = o.predict_woodbury(st, Xs)
+    assert normwise(m1, m2) < 1e-12 and normwise(v1, v2) < 1e-9
+
+
+def test_interpolation_at_small_noise_and_mean_const():
+    rng = np.random.RandomState(4)
+    X = np.sort(rng.rand(30, 1), axis=0); Y = np.sin(6 * X) + 3.0
+    st = o.fit(X, Y, "GPyRBF", 1.0, 0.2, False, 1e-10, mean_const=float(Y.mean()))
+    mean, var = o.predict(st, X, include_noise=False)
+    assert np.abs(mean - Y).max() < 1e-4
+    assert var.max() < 1e-4 and var.min() > -1e-8
+
+
+def test_jitchol_retries_then_raises():
+    A = np.ones((4, 4))          # rank one: dpotrf fails, a jitter of mean(diag)*1e-6 fixes it
+    with pytest.warns(UserWarning):
+        L = o.jitchol(A.copy())
+    assert np.isfinite(L).all()
+    with pytest.raises(np.linalg.LinAlgError):
+        o.jitchol(-np.eye(3))
+
+
+def test_oracle_model_api_shapes():
+    rng = np.random.RandomState(5)
+    X = rng.rand(64, 2); Y = rng.randn(64, 2); Xs = rng.rand(9, 2)
+    m = o.OracleGPModel.from_config({"kernel": {"name": "GPyRBF", "kwargs": {"lengthscale": 0.6, "ARD": True}}, "noise_prior": 0.01})
+    m.init(X, Y)
+    mean, var = m.get_statistics(Xs, full_cov=False)
+    assert mean.shape == (1, 9, 2) and var.shape == (1, 9, 2)
+    mean, cov = m.get_statistics(Xs, full_cov=True)
+    assert cov.shape == (1, 9, 9, 1)
+    e = o.errors(mean[0], np.diagonal(cov[0, :, :, 0])[:, None], rng.randn(9, 2), Y.mean())
+    assert set(e) == {"mae", "max_err", "rmse", "mnlp", "nmse"}

@@ -57,6 +57,8 @@ SIGNATURES = {
     "gpx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "gpx_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "gpx_bytes_allocated": (ctypes.c_int64, [ctypes.c_void_p]),
+    "gpx_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "gpx_gemm_stats": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int64)]),
 }
 
 
@@ -197,6 +199,15 @@ class Handle:
 
     def phase_ms(self):
         return {name: self.lib.gpx_phase_ms(self._h, i) for i, name in enumerate(PHASES)}
+
+    def stream_ptr(self):
+        return int(self.lib.gpx_stream(self._h) or 0)
+
+    def gemm_stats(self):
+        """(device ms, issued fp64 flops, launches) of the DMMA tile-GEMM kernel since the last call."""
+        ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        self._check(self.lib.gpx_gemm_stats(self._h, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)))
+        return ms.value, fl.value, n.value
 
     def launch_count(self):
         return int(self.lib.gpx_launch_count(self._h))

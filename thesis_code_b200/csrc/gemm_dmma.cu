@@ -229,6 +229,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
     }
 }
 
+long long count_valid_tiles(const GemmJob& j) {
+    long long total = 0;
+    for (int c = j.j0; c < j.j1; c++) {
+        int r0 = j.tri ? (j.i0 > c ? j.i0 : c) : j.i0;
+        if (r0 < j.i1) total += j.i1 - r0;
+    }
+    return total;
+}
+
 long long count_slots(const GemmJob& j) {
     long long total = 0;
     for (int c0 = j.j0; c0 < j.j1; c0 += kStrip) {
@@ -247,14 +256,15 @@ void gpx_gemm_init() {
     cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 
-void gpx_launch_gemm(const GemmJob& job, int num_sms, cudaStream_t st, int64_t* launch_counter) {
-    if (job.i1 <= job.i0 || job.j1 <= job.j0 || job.k1 <= job.k0) return;
+long long gpx_launch_gemm(const GemmJob& job, int num_sms, cudaStream_t st, int64_t* launch_counter) {
+    if (job.i1 <= job.i0 || job.j1 <= job.j0 || job.k1 <= job.k0) return 0;
     long long slots = count_slots(job);
-    if (slots <= 0) return;
+    if (slots <= 0) return 0;
     int grid = (int)(slots < num_sms ? slots : num_sms);
     if (job.overwrite)
         gemm_dmma_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(job);
     else
         gemm_dmma_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(job);
     if (launch_counter) (*launch_counter)++;
+    return count_valid_tiles(job) * (job.k1 - job.k0);
 }

@@ -55,6 +55,11 @@ struct gpx_handle {
     int outer_tiles = 4;
     int predict_batch_tiles = 0;  // 0 = auto
     int sync_phases = 1;
+    int gemm_timing = 0;
+    std::vector<cudaEvent_t> gemm_ev;   // pairs, grown on demand
+    size_t gemm_ev_used = 0;
+    double gemm_ms = 0, gemm_flops = 0;
+    int64_t gemm_launches = 0;
 
     // problem
     bool fitted = false;
@@ -157,6 +162,39 @@ int to_device(gpx_t* h, const double* src, size_t count, int mem, DevBuf& stagin
     return 0;
 }
 
+// every DMMA tile-GEMM launch goes through here (optionally bracketed by events for the roofline numbers)
+void gemm(gpx_t* h, const GemmJob& job) {
+    if (!h->gemm_timing) {
+        long long steps = gpx_launch_gemm(job, h->num_sms, h->st, &h->launches);
+        h->gemm_flops += 2.0 * 128 * 128 * 128 * (double)steps;
+        if (steps) h->gemm_launches++;
+        return;
+    }
+    if (h->gemm_ev_used + 2 > h->gemm_ev.size()) {
+        size_t old = h->gemm_ev.size();
+        h->gemm_ev.resize(old + 1024);
+        for (size_t i = old; i < h->gemm_ev.size(); i++) cudaEventCreate(&h->gemm_ev[i]);
+    }
+    cudaEventRecord(h->gemm_ev[h->gemm_ev_used], h->st);
+    long long steps = gpx_launch_gemm(job, h->num_sms, h->st, &h->launches);
+    if (steps) {
+        cudaEventRecord(h->gemm_ev[h->gemm_ev_used + 1], h->st);
+        h->gemm_ev_used += 2;
+        h->gemm_flops += 2.0 * 128 * 128 * 128 * (double)steps;
+        h->gemm_launches++;
+    }
+}
+
+// fold the recorded per-launch event pairs into gemm_ms (the stream must be idle)
+void gemm_collect(gpx_t* h) {
+    for (size_t i = 0; i + 1 < h->gemm_ev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->gemm_ev[i], h->gemm_ev[i + 1]) == cudaSuccess) h->gemm_ms += ms;
+        else cudaGetLastError();
+    }
+    h->gemm_ev_used = 0;
+}
+
 TileMat lmat(gpx_t* h) { return TileMat{ptr<double>(h->L), ptr<int64_t>(h->coloff), 1}; }
 TileMat linvmat(gpx_t* h) { return TileMat{ptr<double>(h->linv), ptr<int64_t>(h->linv_coloff), 1}; }
 
@@ -178,7 +216,7 @@ int cholesky(gpx_t* h) {
                 t.A = L; t.B = Li; t.C = L;
                 t.tri = 0; t.i0 = k + 1; t.i1 = nt; t.j0 = k; t.j1 = k + 1; t.k0 = k; t.k1 = k + 1;
                 t.bdiag = 1; t.overwrite = 1;
-                gpx_launch_gemm(t, h->num_sms, h->st, &h->launches);
+                gemm(h, t);
             }
             if (k + 1 < p1) {
                 // update the remaining columns of this outer panel with column k
@@ -186,7 +224,7 @@ int cholesky(gpx_t* h) {
                 u.A = L; u.B = L; u.C = L;
                 u.tri = 1; u.i0 = k + 1; u.i1 = nt; u.j0 = k + 1; u.j1 = p1; u.k0 = k; u.k1 = k + 1;
                 u.bdiag = 0; u.overwrite = 0;
-                gpx_launch_gemm(u, h->num_sms, h->st, &h->launches);
+                gemm(h, u);
             }
         }
         if (p1 < nt) {
@@ -194,7 +232,7 @@ int cholesky(gpx_t* h) {
             u.A = L; u.B = L; u.C = L;
             u.tri = 1; u.i0 = p1; u.i1 = nt; u.j0 = p1; u.j1 = nt; u.k0 = p0; u.k1 = p1;
             u.bdiag = 0; u.overwrite = 0;
-            gpx_launch_gemm(u, h->num_sms, h->st, &h->launches);
+            gemm(h, u);
         }
     }
     return 0;
@@ -243,6 +281,7 @@ void gpx_destroy(gpx_t* h) {
     for (DevBuf* b : all) release(h, *b);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (auto& e : h->ev) cudaEventDestroy(e);
+    for (auto& e : h->gemm_ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->st);
     delete h;
 }
@@ -264,6 +303,7 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "outer_tiles")) { if (value < 1 || value > 64) return fail(h, -1, "outer_tiles out of range"); h->outer_tiles = (int)value; return 0; }
     if (!strcmp(name, "predict_batch_tiles")) { if (value < 0) return fail(h, -1, "bad predict_batch_tiles"); h->predict_batch_tiles = (int)value; return 0; }
     if (!strcmp(name, "sync_phases")) { h->sync_phases = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "gemm_timing")) { h->gemm_timing = value ? 1 : 0; return 0; }
     return fail(h, -1, "unknown option %s", name);
 }
 
@@ -272,6 +312,18 @@ double gpx_phase_ms(const gpx_t* h, int phase) {
     return h->phase_ms[phase];
 }
 int64_t gpx_launch_count(const gpx_t* h) { return h ? h->launches : -1; }
+void* gpx_stream(const gpx_t* h) { return h ? (void*)h->st : nullptr; }
+int gpx_gemm_stats(gpx_t* h, double* total_ms, double* issued_flops, int64_t* launches) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->st);
+    gemm_collect(h);
+    if (total_ms) *total_ms = h->gemm_ms;
+    if (issued_flops) *issued_flops = h->gemm_flops;
+    if (launches) *launches = h->gemm_launches;
+    h->gemm_ms = 0; h->gemm_flops = 0; h->gemm_launches = 0;
+    return 0;
+}
 int64_t gpx_bytes_allocated(const gpx_t* h) { return h ? h->bytes_alloc : -1; }
 
 int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O, int kernel_id, double variance,
@@ -372,6 +424,7 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, -2, "CUDA launch error during fit: %s", cudaGetErrorString(e));
     for (int ph : {GPX_PHASE_H2D, GPX_PHASE_KBUILD, GPX_PHASE_CHOLESKY, GPX_PHASE_SOLVE, GPX_PHASE_LML}) phase_collect(h, ph);
+    gemm_collect(h);
     if (hinfo != 0) {
         fail(h, hinfo, "Ky is not positive definite: non-positive pivot at row %d", hinfo);
         return hinfo;
@@ -404,19 +457,19 @@ static void var_trsm(gpx_t* h, TileMat Tt, int nbt) {
             GemmJob t{};
             t.A = Tt; t.B = Li; t.C = Tt;
             t.tri = 0; t.i0 = 0; t.i1 = nbt; t.j0 = k; t.j1 = k + 1; t.k0 = k; t.k1 = k + 1; t.bdiag = 1; t.overwrite = 1;
-            gpx_launch_gemm(t, h->num_sms, h->st, &h->launches);
+            gemm(h, t);
             if (k + 1 < p1) {
                 GemmJob u{};
                 u.A = Tt; u.B = L; u.C = Tt;
                 u.tri = 0; u.i0 = 0; u.i1 = nbt; u.j0 = k + 1; u.j1 = p1; u.k0 = k; u.k1 = k + 1; u.bdiag = 0; u.overwrite = 0;
-                gpx_launch_gemm(u, h->num_sms, h->st, &h->launches);
+                gemm(h, u);
             }
         }
         if (p1 < nt) {
             GemmJob u{};
             u.A = Tt; u.B = L; u.C = Tt;
             u.tri = 0; u.i0 = 0; u.i1 = nbt; u.j0 = p1; u.j1 = nt; u.k0 = p0; u.k1 = p1; u.bdiag = 0; u.overwrite = 0;
-            gpx_launch_gemm(u, h->num_sms, h->st, &h->launches);
+            gemm(h, u);
         }
     }
 }
@@ -523,6 +576,7 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
     if (e != cudaSuccess) return fail(h, -2, "CUDA launch error during predict: %s", cudaGetErrorString(e));
     phase_collect(h, GPX_PHASE_H2D);
     if (mem == GPX_MEM_HOST) phase_collect(h, GPX_PHASE_D2H);
+    gemm_collect(h);
     return 0;
 }
 

@@ -71,7 +71,8 @@ struct GemmJob {
     int bdiag;         // 1: B tile index is (k, k) regardless of J (TRSM with an inverted diagonal tile)
     int overwrite;     // 1: C = +A*B^T ; 0: C -= A*B^T
 };
-void gpx_launch_gemm(const GemmJob& job, int num_sms, cudaStream_t st, int64_t* launch_counter);
+// returns the number of (tile, k-tile) steps the launch performs (each is 2*128^3 flop); 0 if nothing was launched
+long long gpx_launch_gemm(const GemmJob& job, int num_sms, cudaStream_t st, int64_t* launch_counter);
 void gpx_gemm_init();  // sets the dynamic shared memory attribute
 
 void gpx_launch_potrf_tile(double* tile, double* inv_tile, int* info, int col_index, cudaStream_t st);
