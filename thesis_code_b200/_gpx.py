@@ -123,6 +123,7 @@ class Handle:
 
     def comm_init(self, rank, world, uid):
         self._check(self.lib.gpx_comm_init(self._h, int(rank), int(world), uid))
+        self.rank, self.world = int(rank), int(world)
 
     # ---- host (numpy) entry points -----------------------------------------------------------------------
     def fit(self, X, Y, kernel_id, variance, lengthscale, noise, jitter=1e-8, mean_const=0.0):

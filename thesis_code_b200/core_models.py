@@ -205,6 +205,12 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
     def _get_handle(self):
         if self._handle is None:
             self._handle = _gpx.Handle(self.device if self.device is not None else _default_device())
+            # one process per GPU: when torch.distributed is up (torchrun), shard the factor over the ranks
+            if os.environ.get("GPX_DISTRIBUTED", "1") != "0" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    from . import distributed as gdist
+                    gdist.init_handle_comm(self._handle, dist)
         return self._handle
 
     def _factorize(self):

@@ -73,37 +73,39 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
-// Output-tile enumeration shared by producer and consumers: strips of kStrip tile columns, row-major inside a
-// strip, so the CTAs running together share few operand panels (L2 reuse).  Invalid (above-diagonal) slots of a
-// triangular job are skipped.
+// Output-tile enumeration shared by producer and consumers: strips of kStrip column ordinals, row-major inside a
+// strip, so CTAs running together share few operand panels (L2 reuse).  Invalid (above-diagonal) slots of a
+// triangular job are skipped.  A CTA owns `chunk` consecutive slots; grids larger than the SM count are scheduled
+// by the hardware as earlier CTAs retire, which balances the ragged triangular jobs and lets kernels of other
+// streams (panel factorisation, NCCL) interleave.
 struct TileWalk {
-    int tri, i0, i1, j0, j1;
-    int strip_c0, strip_w, strip_r0;
+    int tri, i0, i1, ncols;
+    int strip_m0, strip_w, strip_r0;
     long long strip_begin, strip_end;
+    __device__ void set_strip(const GemmJob& j) {
+        strip_w = min(kStrip, ncols - strip_m0);
+        strip_r0 = tri ? max(i0, gpx_job_col(j, strip_m0)) : i0;
+        if (strip_r0 > i1) strip_r0 = i1;
+    }
     __device__ void init(const GemmJob& j) {
-        tri = j.tri; i0 = j.i0; i1 = j.i1; j0 = j.j0; j1 = j.j1;
-        strip_c0 = j0;
-        set_strip();
+        tri = j.tri; i0 = j.i0; i1 = j.i1; ncols = j.ncols;
+        strip_m0 = 0;
+        set_strip(j);
         strip_begin = 0;
         strip_end = (long long)(i1 - strip_r0) * strip_w;
     }
-    __device__ void set_strip() {
-        strip_w = min(kStrip, j1 - strip_c0);
-        strip_r0 = tri ? max(i0, strip_c0) : i0;
-        if (strip_r0 > i1) strip_r0 = i1;
-    }
     // returns false when t is past the end; sets I,J and valid
-    __device__ bool locate(long long t, int& I, int& J, bool& valid) {
+    __device__ bool locate(const GemmJob& j, long long t, int& I, int& J, bool& valid) {
         while (t >= strip_end) {
-            strip_c0 += strip_w;
-            if (strip_c0 >= j1) return false;
-            set_strip();
+            strip_m0 += strip_w;
+            if (strip_m0 >= ncols) return false;
+            set_strip(j);
             strip_begin = strip_end;
             strip_end = strip_begin + (long long)(i1 - strip_r0) * strip_w;
         }
         long long u = t - strip_begin;
         I = strip_r0 + (int)(u / strip_w);
-        J = strip_c0 + (int)(u % strip_w);
+        J = gpx_job_col(j, strip_m0 + (int)(u % strip_w));
         valid = !tri || I >= J;
         return true;
     }
@@ -127,13 +129,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
     int stage = 0;
     uint32_t phase = 0;
     const int nslice = GPX_TILE / kStageK;  // 8 slices per operand tile
+    const long long t_begin = (long long)blockIdx.x * job.chunk, t_end = t_begin + job.chunk;
 
     if (warp == kConsumerWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
-            for (long long t = blockIdx.x;; t += gridDim.x) {
+            for (long long t = t_begin; t < t_end; t++) {
                 int I, J; bool valid;
-                if (!walk.locate(t, I, J, valid)) break;
+                if (!walk.locate(job, t, I, J, valid)) break;
                 if (!valid) continue;
                 for (int kb = job.k0; kb < job.k1; kb++) {
                     const double* a = tile_ptr(job.A, I, kb);
@@ -159,9 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
         // accumulator fragment (i,j) lives at tile offset  ((wn*32 + j*8) >> 3) * 1024 + (wm*64 + i*8 + g) * 8 + 2*tq
         const int c_off = (wn * 4) * 1024 + (wm * 64 + g) * 8 + 2 * tq;
 
-        for (long long t = blockIdx.x;; t += gridDim.x) {
+        for (long long t = t_begin; t < t_end; t++) {
             int I, J; bool valid;
-            if (!walk.locate(t, I, J, valid)) break;
+            if (!walk.locate(job, t, I, J, valid)) break;
             if (!valid) continue;
             double* ctile = tile_ptr(job.C, I, J);
             double acc[8][4][2];
@@ -231,7 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
 
 long long count_valid_tiles(const GemmJob& j) {
     long long total = 0;
-    for (int c = j.j0; c < j.j1; c++) {
+    for (int m = 0; m < j.ncols; m++) {
+        int c = gpx_job_col(j, m);
         int r0 = j.tri ? (j.i0 > c ? j.i0 : c) : j.i0;
         if (r0 < j.i1) total += j.i1 - r0;
     }
@@ -240,8 +244,9 @@ long long count_valid_tiles(const GemmJob& j) {
 
 long long count_slots(const GemmJob& j) {
     long long total = 0;
-    for (int c0 = j.j0; c0 < j.j1; c0 += kStrip) {
-        int w = (j.j1 - c0 < kStrip) ? (j.j1 - c0) : kStrip;
+    for (int m0 = 0; m0 < j.ncols; m0 += kStrip) {
+        int w = (j.ncols - m0 < kStrip) ? (j.ncols - m0) : kStrip;
+        int c0 = gpx_job_col(j, m0);
         int r0 = j.tri ? (j.i0 > c0 ? j.i0 : c0) : j.i0;
         if (r0 > j.i1) r0 = j.i1;
         total += (long long)(j.i1 - r0) * w;
@@ -256,11 +261,17 @@ void gpx_gemm_init() {
     cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 
-long long gpx_launch_gemm(const GemmJob& job, int num_sms, cudaStream_t st, int64_t* launch_counter) {
-    if (job.i1 <= job.i0 || job.j1 <= job.j0 || job.k1 <= job.k0) return 0;
+long long gpx_launch_gemm(const GemmJob& job_in, int num_sms, cudaStream_t st, int64_t* launch_counter) {
+    GemmJob job = job_in;
+    if (job.i1 <= job.i0 || job.ncols <= 0 || job.k1 <= job.k0) return 0;
     long long slots = count_slots(job);
     if (slots <= 0) return 0;
-    int grid = (int)(slots < num_sms ? slots : num_sms);
+    // <= num_sms slots: one per CTA.  Otherwise chunks of up to 8 consecutive slots (a strip row), >= one wave of CTAs.
+    long long chunk = slots / (2LL * num_sms);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 8) chunk = 8;
+    job.chunk = (int)chunk;
+    int grid = (int)((slots + chunk - 1) / chunk);
     if (job.overwrite)
         gemm_dmma_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(job);
     else

@@ -1,10 +1,26 @@
 // C ABI (include/gpx.h) and host-side orchestration of the exact-GP hot path.
 //
-// The handle owns: the scaled training inputs, the packed lower-triangular tile storage of Ky (factored in place
-// into L), the inverted diagonal tiles, alpha, the predict workspaces and one CUDA stream.  The blocked
-// right-looking Cholesky is driven from here: per tile column  POTRF(tile) -> TRSM (DMMA GEMM against the inverted
-// tile) -> rank-128 update of the rest of the current outer panel; per outer panel one SYRK/GEMM trailing update
-// with K = outer_tiles*128 (all DMMA).  See DESIGN.md.
+// One handle = one process = one GPU.  The handle owns the scaled training inputs, its shard of the packed
+// lower-triangular tile storage of Ky (factored in place into L), all inverted diagonal tiles, alpha, the predict
+// workspaces, three CUDA streams and (world > 1) an NCCL communicator plus two panel receive buffers.
+//
+// Distribution: tile columns are grouped into outer panels of `outer_tiles` columns; panel p is
+// owned by rank p % world (1-D block-column-cyclic).  world == 1 is the same code with every panel owned.
+//
+// Cholesky (right-looking, look-ahead depth 1), per panel p:
+//   owner, stream F (high priority): POTRF(tile) -> TRSM (DMMA GEMM vs the inverted tile) -> rank-128 updates inside
+//          the panel, column by column;
+//   stream C (high priority): ncclBroadcast of the factored panel (+ its inverted diagonal tiles) from the owner;
+//   every rank, stream U: (a) the update of the NEXT panel's columns if this rank owns it -- which releases stream F
+//          to factor panel p+1 --, the forward-substitution steps of the alpha solve with the panel (fused: the panel
+//          is read while it is hot), and (b) the SYRK/GEMM update of the rest of the owned columns, K = panel.
+//   So panel p+1 is factored and broadcast while update (b) of panel p is still running.
+// Backward substitution: row-oriented, z_J lives with the owner of column J; one 4 KB broadcast of alpha per panel.
+// Predict: test tiles are sharded over ranks; the panels of L are re-broadcast (double buffered) while each rank runs
+// its K*-build + blocked triangular solve + row sum-of-squares; results are combined with one small all-reduce.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -27,10 +43,10 @@ void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, double prior_var, double
 void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double* out, cudaStream_t st);
 void gpx_launch_fwd_step(TileMat L, const double* linv, int nt, int J, double* b, double* z, int64_t Np, int O,
                          int max_ctas, cudaStream_t st);
-void gpx_launch_bwd_step(TileMat L, const double* linv, int I, double* z, double* a, int64_t Np, int O, int max_ctas,
-                         cudaStream_t st);
-void gpx_launch_lml(TileMat L, int nt, const int* owned, const double* alpha, const double* resid, int64_t Np, int O,
-                    double* out2, cudaStream_t st);
+void gpx_launch_bwd_step(TileMat L, const double* linv, int I, double* z, double* a, int64_t Np, int O,
+                         int compute_alpha, int ncols, int jbase, int jW, int jstride, int max_ctas, cudaStream_t st);
+void gpx_launch_lml(const double* linv, const double* alpha, const double* resid, int64_t Np, int O, double* out2,
+                    cudaStream_t st);
 void gpx_launch_resid(const double* Y, int64_t N, int64_t Np, int O, double mean_const, double* resid, cudaStream_t st);
 void gpx_launch_untranspose(const double* in, int64_t N, int64_t Np, int O, double* out, cudaStream_t st);
 
@@ -41,22 +57,69 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+// NCCL is resolved at run time (dlopen) so that the library also loads where no libnccl is installed; the
+// single-GPU path never touches it.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool tried = false, ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.tried) return api;
+    api.tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return api;
+#define GPX_SYM(field, name) *(void**)(&api.field) = dlsym(api.lib, name)
+    GPX_SYM(GetUniqueId, "ncclGetUniqueId");
+    GPX_SYM(CommInitRank, "ncclCommInitRank");
+    GPX_SYM(CommDestroy, "ncclCommDestroy");
+    GPX_SYM(Broadcast, "ncclBroadcast");
+    GPX_SYM(AllReduce, "ncclAllReduce");
+    GPX_SYM(GroupStart, "ncclGroupStart");
+    GPX_SYM(GroupEnd, "ncclGroupEnd");
+    GPX_SYM(GetErrorString, "ncclGetErrorString");
+#undef GPX_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.AllReduce &&
+             api.GroupStart && api.GroupEnd && api.GetErrorString;
+    return api;
+}
+
 }  // namespace
 
 struct gpx_handle {
     int device = 0;
     int num_sms = 148;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;    // main / update stream (U)
+    cudaStream_t st_f = nullptr;  // panel factorisation (F), high priority
+    cudaStream_t st_c = nullptr;  // communication (C), high priority
     std::string err;
     int64_t launches = 0;
     int64_t bytes_alloc = 0;
+
+    // distribution
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
 
     // options
     int outer_tiles = 4;
     int predict_batch_tiles = 0;  // 0 = auto
     int sync_phases = 1;
     int gemm_timing = 0;
-    std::vector<cudaEvent_t> gemm_ev;   // pairs, grown on demand
+    int lookahead = 1;
+    std::vector<cudaEvent_t> gemm_ev;  // pairs, grown on demand
     size_t gemm_ev_used = 0;
     double gemm_ms = 0, gemm_flops = 0;
     int64_t gemm_launches = 0;
@@ -65,14 +128,16 @@ struct gpx_handle {
     bool fitted = false;
     int64_t N = 0, Np = 0;
     int nt = 0, d = 0, O = 0, kernel_id = 0, n_ls = 0;
+    int W = 4, npanels = 0;  // W = outer_tiles frozen at fit time
     double variance = 1, noise = 1, jitter = 1e-8, mean_const = 0;
     double lml = 0, logdet = 0, quad = 0;
 
-    DevBuf Xs, xsq, ls, L, linv, coloff, linv_coloff, resid, work1, work2, alpha, scal, info;
-    DevBuf stage;  // device staging for host inputs / outputs
-    std::vector<int64_t> h_coloff;
-    void* pinned = nullptr;
-    size_t pinned_bytes = 0;
+    DevBuf Xs, xsq, ls, L, linv, coloff, vcoloff, linv_coloff, resid, work1, work2, alpha, scal, info;
+    DevBuf stage;
+    DevBuf pbuf[2];                     // panel receive buffers (world > 1)
+    std::vector<int64_t> h_coloff;      // local offsets (-1: not owned)
+    std::vector<int64_t> h_vcoloff;     // virtual full packed offsets
+    std::vector<cudaEvent_t> pev;       // per-panel events (3 per panel), no timing
 
     // predict workspaces
     DevBuf Tt, tt_coloff, Xt, xtsq, mean_partial, dmean, dvar;
@@ -93,11 +158,18 @@ int fail(gpx_t* h, int code, const char* fmt, ...) {
     return code;
 }
 
-#define GPX_CUDA(h, call)                                                                              \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess) return fail(h, -2, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), \
-                                           __FILE__, __LINE__, #call);                                 \
+#define GPX_CUDA(h, call)                                                                                \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(h, -2, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+    } while (0)
+
+#define GPX_NCCL(h, call)                                                                                \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess)                                                                           \
+            return fail(h, -7, "NCCL error %s at %s:%d (%s)", nccl().GetErrorString(r_), __FILE__, __LINE__, #call); \
     } while (0)
 
 int ensure(gpx_t* h, DevBuf& b, size_t bytes) {
@@ -128,16 +200,6 @@ void release(gpx_t* h, DevBuf& b) {
     b.bytes = 0;
 }
 
-int ensure_pinned(gpx_t* h, size_t bytes) {
-    if (h->pinned_bytes >= bytes) return 0;
-    if (h->pinned) cudaFreeHost(h->pinned);
-    h->pinned = nullptr;
-    h->pinned_bytes = 0;
-    GPX_CUDA(h, cudaMallocHost(&h->pinned, bytes));
-    h->pinned_bytes = bytes;
-    return 0;
-}
-
 template <typename T>
 T* ptr(const DevBuf& b) { return reinterpret_cast<T*>(b.p); }
 
@@ -150,22 +212,21 @@ void phase_collect(gpx_t* h, int ph) {
     else cudaGetLastError();
 }
 
-// stage a caller buffer onto the device (host -> pinned -> device, or device pointer passthrough)
+// stage a caller buffer onto the device (host pointer -> device copy on the main stream, or passthrough)
 int to_device(gpx_t* h, const double* src, size_t count, int mem, DevBuf& staging, const double** out) {
     if (mem == GPX_MEM_DEVICE) { *out = src; return 0; }
     size_t bytes = count * sizeof(double);
     int rc = ensure(h, staging, bytes);
     if (rc) return rc;
-    // pageable numpy memory: cudaMemcpyAsync stages through the driver's pinned buffers; one copy per input
     GPX_CUDA(h, cudaMemcpyAsync(staging.p, src, bytes, cudaMemcpyHostToDevice, h->st));
     *out = ptr<double>(staging);
     return 0;
 }
 
 // every DMMA tile-GEMM launch goes through here (optionally bracketed by events for the roofline numbers)
-void gemm(gpx_t* h, const GemmJob& job) {
+void gemm(gpx_t* h, const GemmJob& job, cudaStream_t st) {
     if (!h->gemm_timing) {
-        long long steps = gpx_launch_gemm(job, h->num_sms, h->st, &h->launches);
+        long long steps = gpx_launch_gemm(job, h->num_sms, st, &h->launches);
         h->gemm_flops += 2.0 * 128 * 128 * 128 * (double)steps;
         if (steps) h->gemm_launches++;
         return;
@@ -175,17 +236,18 @@ void gemm(gpx_t* h, const GemmJob& job) {
         h->gemm_ev.resize(old + 1024);
         for (size_t i = old; i < h->gemm_ev.size(); i++) cudaEventCreate(&h->gemm_ev[i]);
     }
-    cudaEventRecord(h->gemm_ev[h->gemm_ev_used], h->st);
-    long long steps = gpx_launch_gemm(job, h->num_sms, h->st, &h->launches);
+    cudaEventRecord(h->gemm_ev[h->gemm_ev_used], st);
+    long long steps = gpx_launch_gemm(job, h->num_sms, st, &h->launches);
     if (steps) {
-        cudaEventRecord(h->gemm_ev[h->gemm_ev_used + 1], h->st);
+        cudaEventRecord(h->gemm_ev[h->gemm_ev_used + 1], st);
         h->gemm_ev_used += 2;
         h->gemm_flops += 2.0 * 128 * 128 * 128 * (double)steps;
         h->gemm_launches++;
     }
 }
 
-// fold the recorded per-launch event pairs into gemm_ms (the stream must be idle)
+// fold the recorded per-launch event pairs into gemm_ms (all streams must be idle).  With look-ahead the panel
+// kernels of stream F overlap the updates of stream U, so the sum can exceed the wall time of the phase.
 void gemm_collect(gpx_t* h) {
     for (size_t i = 0; i + 1 < h->gemm_ev_used; i += 2) {
         float ms = 0.f;
@@ -195,44 +257,211 @@ void gemm_collect(gpx_t* h) {
     h->gemm_ev_used = 0;
 }
 
+// ---- distribution helpers ---------------------------------------------------------------------------------------
+inline int panel_begin(const gpx_t* h, int p) { return p * h->W; }
+inline int panel_end(const gpx_t* h, int p) { int e = (p + 1) * h->W; return e < h->nt ? e : h->nt; }
+inline int panel_owner(const gpx_t* h, int p) { return p % h->world; }
+inline bool owns_panel(const gpx_t* h, int p) { return panel_owner(h, p) == h->rank; }
+inline int64_t panel_elems(const gpx_t* h, int p) {
+    int64_t e = 0;
+    for (int c = panel_begin(h, p); c < panel_end(h, p); c++) e += (int64_t)(h->nt - c) * GPX_TILE_ELEMS;
+    return e;
+}
+// first panel >= q owned by this rank (may be >= npanels)
+inline int next_owned_panel(const gpx_t* h, int q) {
+    int r = q % h->world;
+    int add = (h->rank - r + h->world) % h->world;
+    return q + add;
+}
+// number of tile columns in owned panels q, q+world, q+2 world, ... (q must be owned)
+inline int owned_cols_from(const gpx_t* h, int q) {
+    int n = 0;
+    for (int p = q; p < h->npanels; p += h->world) n += panel_end(h, p) - panel_begin(h, p);
+    return n;
+}
+
+// receive buffers alternate over the panels this rank does NOT own
+inline int recv_index(const gpx_t* h, int p) {
+    int owned_before = (p > h->rank) ? (p - h->rank + h->world - 1) / h->world : 0;
+    return p - owned_before;
+}
+inline double* recv_buf(gpx_t* h, int p) { return reinterpret_cast<double*>(h->pbuf[recv_index(h, p) & 1].p); }
+// the previous non-owned panel that used the same receive buffer as panel p (-1: none)
+inline int prev_same_buffer_panel(const gpx_t* h, int p) {
+    int seen = 0;
+    for (int q = p - 1; q >= 0; q--) {
+        if (!owns_panel(h, q) && ++seen == 2) return q;
+    }
+    return -1;
+}
+
 TileMat lmat(gpx_t* h) { return TileMat{ptr<double>(h->L), ptr<int64_t>(h->coloff), 1}; }
 TileMat linvmat(gpx_t* h) { return TileMat{ptr<double>(h->linv), ptr<int64_t>(h->linv_coloff), 1}; }
+// the factored panel p as an operand: the local storage on its owner, the receive buffer elsewhere
+TileMat panel_mat(gpx_t* h, int p) {
+    if (owns_panel(h, p)) return lmat(h);
+    return TileMat{recv_buf(h, p) - h->h_vcoloff[panel_begin(h, p)], ptr<int64_t>(h->vcoloff), 1};
+}
 
-// ---- blocked right-looking Cholesky of the packed tile storage (in place) -------------------------------------
-int cholesky(gpx_t* h) {
-    const int nt = h->nt;
+cudaEvent_t pevent(gpx_t* h, int p, int which) { return h->pev[(size_t)3 * p + which]; }  // 0 ready, 1 a-done, 2 upd-done
+
+int ensure_panel_events(gpx_t* h, int npanels) {
+    size_t need = (size_t)3 * npanels;
+    while (h->pev.size() < need) {
+        cudaEvent_t e;
+        GPX_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pev.push_back(e);
+    }
+    return 0;
+}
+
+// broadcast panel p (its packed columns and, optionally, its inverted diagonal tiles) from its owner, on stream C
+int broadcast_panel(gpx_t* h, int p, bool with_linv) {
+    const int p0 = panel_begin(h, p), p1 = panel_end(h, p), root = panel_owner(h, p);
+    const int64_t elems = panel_elems(h, p);
+    double* buf = owns_panel(h, p) ? ptr<double>(h->L) + h->h_coloff[p0] : recv_buf(h, p);
+    GPX_NCCL(h, nccl().GroupStart());
+    ncclResult_t r1 = nccl().Broadcast(buf, buf, (size_t)elems, ncclDouble, root, h->comm, h->st_c);
+    ncclResult_t r2 = ncclSuccess;
+    if (with_linv) {
+        double* li = ptr<double>(h->linv) + (int64_t)p0 * GPX_TILE_ELEMS;
+        r2 = nccl().Broadcast(li, li, (size_t)(p1 - p0) * GPX_TILE_ELEMS, ncclDouble, root, h->comm, h->st_c);
+    }
+    GPX_NCCL(h, nccl().GroupEnd());
+    GPX_NCCL(h, r1);
+    GPX_NCCL(h, r2);
+    return 0;
+}
+
+// factor panel p in place on its owner (stream F)
+void factor_panel(gpx_t* h, int p) {
+    const int nt = h->nt, p0 = panel_begin(h, p), p1 = panel_end(h, p);
     TileMat L = lmat(h), Li = linvmat(h);
     int* info = ptr<int>(h->info);
-    const int W = h->outer_tiles < 1 ? 1 : h->outer_tiles;
-    for (int p0 = 0; p0 < nt; p0 += W) {
-        const int p1 = (p0 + W < nt) ? p0 + W : nt;
-        for (int k = p0; k < p1; k++) {
-            double* diag = ptr<double>(h->L) + h->h_coloff[k];
-            gpx_launch_potrf_tile(diag, ptr<double>(h->linv) + (int64_t)k * GPX_TILE_ELEMS, info, k, h->st);
-            h->launches++;
-            if (k + 1 < nt) {
-                // TRSM: L(I,k) <- L(I,k) * Linv_k^T for I > k
-                GemmJob t{};
-                t.A = L; t.B = Li; t.C = L;
-                t.tri = 0; t.i0 = k + 1; t.i1 = nt; t.j0 = k; t.j1 = k + 1; t.k0 = k; t.k1 = k + 1;
-                t.bdiag = 1; t.overwrite = 1;
-                gemm(h, t);
+    for (int k = p0; k < p1; k++) {
+        double* diag = ptr<double>(h->L) + h->h_coloff[k];
+        gpx_launch_potrf_tile(diag, ptr<double>(h->linv) + (int64_t)k * GPX_TILE_ELEMS, info, k, h->st_f);
+        h->launches++;
+        if (k + 1 < nt) {
+            GemmJob t{};  // TRSM: L(I,k) <- L(I,k) * Linv_k^T for I > k
+            t.A = L; t.B = Li; t.C = L;
+            t.tri = 0; t.i0 = k + 1; t.i1 = nt; t.ncols = 1; t.jbase = k; t.jW = GPX_JW_CONTIG; t.jstride = 0;
+            t.k0 = k; t.k1 = k + 1; t.bdiag = 1; t.overwrite = 1;
+            gemm(h, t, h->st_f);
+        }
+        if (k + 1 < p1) {
+            GemmJob u{};  // update the remaining columns of this panel with column k
+            u.A = L; u.B = L; u.C = L;
+            u.tri = 1; u.i0 = k + 1; u.i1 = nt; u.ncols = p1 - (k + 1); u.jbase = k + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+            u.k0 = k; u.k1 = k + 1; u.bdiag = 0; u.overwrite = 0;
+            gemm(h, u, h->st_f);
+        }
+    }
+}
+
+// blocked right-looking Cholesky with look-ahead + fused forward substitution.  b (work1) is consumed, z -> work2.
+int cholesky(gpx_t* h) {
+    const int nt = h->nt, np = h->npanels, G = h->world, W = h->W;
+    const int max_ctas = 2 * h->num_sms;
+    int rc = ensure_panel_events(h, np);
+    if (rc) return rc;
+    cudaEvent_t ev_start;  // everything enqueued on the main stream so far (K-build, residual) is done
+    GPX_CUDA(h, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    GPX_CUDA(h, cudaEventRecord(ev_start, h->st));
+    GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, ev_start, 0));
+    GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, ev_start, 0));
+    for (int p = 0; p < np; p++) {
+        const int p0 = panel_begin(h, p), p1 = panel_end(h, p);
+        const bool own = owns_panel(h, p);
+        if (own) {
+            if (p > 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, pevent(h, p - 1, 1), 0));
+            factor_panel(h, p);
+            GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_f));
+            if (G > 1) {
+                GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, p, 0), 0));
+                if ((rc = broadcast_panel(h, p, true))) return rc;
             }
-            if (k + 1 < p1) {
-                // update the remaining columns of this outer panel with column k
-                GemmJob u{};
-                u.A = L; u.B = L; u.C = L;
-                u.tri = 1; u.i0 = k + 1; u.i1 = nt; u.j0 = k + 1; u.j1 = p1; u.k0 = k; u.k1 = k + 1;
-                u.bdiag = 0; u.overwrite = 0;
-                gemm(h, u);
+        } else {
+            const int q = prev_same_buffer_panel(h, p);
+            if (q >= 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, q, 2), 0));  // receive buffer is free
+            if ((rc = broadcast_panel(h, p, true))) return rc;
+            GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_c));
+        }
+        // ---- stream U: consume panel p ----
+        GPX_CUDA(h, cudaStreamWaitEvent(h->st, pevent(h, p, 0), 0));
+        TileMat P = panel_mat(h, p);
+        const int q1 = next_owned_panel(h, p + 1);
+        // (a) the next panel's columns first when this rank owns them: that is what stream F waits for
+        int qb = q1;
+        if (q1 == p + 1 && q1 < np) {
+            GemmJob a{};
+            a.A = P; a.B = P; a.C = lmat(h);
+            a.tri = 1; a.i0 = p1; a.i1 = nt; a.ncols = panel_end(h, q1) - panel_begin(h, q1); a.jbase = panel_begin(h, q1);
+            a.jW = GPX_JW_CONTIG; a.jstride = 0; a.k0 = p0; a.k1 = p1; a.bdiag = 0; a.overwrite = 0;
+            gemm(h, a, h->st);
+            GPX_CUDA(h, cudaEventRecord(pevent(h, p, 1), h->st));
+            qb = q1 + G;
+        }
+        // fused forward substitution with the columns of this panel (replicated right-hand side)
+        for (int J = p0; J < p1; J++) {
+            gpx_launch_fwd_step(P, ptr<double>(h->linv), nt, J, ptr<double>(h->work1), ptr<double>(h->work2), h->Np, h->O,
+                                max_ctas, h->st);
+            h->launches++;
+        }
+        // (b) the rest of the owned columns
+        if (qb < np) {
+            GemmJob b{};
+            b.A = P; b.B = P; b.C = lmat(h);
+            b.tri = 1; b.i0 = p1; b.i1 = nt; b.ncols = owned_cols_from(h, qb); b.jbase = panel_begin(h, qb);
+            b.jW = W; b.jstride = W * G; b.k0 = p0; b.k1 = p1; b.bdiag = 0; b.overwrite = 0;
+            gemm(h, b, h->st);
+        }
+        GPX_CUDA(h, cudaEventRecord(pevent(h, p, 2), h->st));
+        if (!h->lookahead) {  // debugging aid: serialise the three streams
+            GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, pevent(h, p, 2), 0));
+            GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, p, 2), 0));
+        }
+    }
+    // join F and C into the main stream
+    cudaEvent_t ev_f, ev_c;
+    GPX_CUDA(h, cudaEventCreateWithFlags(&ev_f, cudaEventDisableTiming));
+    GPX_CUDA(h, cudaEventCreateWithFlags(&ev_c, cudaEventDisableTiming));
+    GPX_CUDA(h, cudaEventRecord(ev_f, h->st_f));
+    GPX_CUDA(h, cudaEventRecord(ev_c, h->st_c));
+    GPX_CUDA(h, cudaStreamWaitEvent(h->st, ev_f, 0));
+    GPX_CUDA(h, cudaStreamWaitEvent(h->st, ev_c, 0));
+    cudaEventDestroy(ev_start);
+    cudaEventDestroy(ev_f);
+    cudaEventDestroy(ev_c);
+    return 0;
+}
+
+// backward substitution L^T alpha = z (z in work2, replicated after the fused forward pass)
+int backward_solve(gpx_t* h) {
+    const int np = h->npanels, G = h->world, W = h->W;
+    const int max_ctas = 2 * h->num_sms;
+    const int q0 = next_owned_panel(h, 0);
+    const int ncols_owned = q0 < np ? owned_cols_from(h, q0) : 0;
+    const int jbase = q0 < np ? panel_begin(h, q0) : 0;
+    for (int p = np - 1; p >= 0; p--) {
+        const int p0 = panel_begin(h, p), p1 = panel_end(h, p);
+        const bool own = owns_panel(h, p);
+        if (!own) {
+            for (int o = 0; o < h->O; o++) {
+                double* a = ptr<double>(h->alpha) + (int64_t)o * h->Np + (int64_t)p0 * GPX_TILE;
+                GPX_NCCL(h, nccl().Broadcast(a, a, (size_t)(p1 - p0) * GPX_TILE, ncclDouble, panel_owner(h, p), h->comm, h->st));
             }
         }
-        if (p1 < nt) {
-            GemmJob u{};
-            u.A = L; u.B = L; u.C = L;
-            u.tri = 1; u.i0 = p1; u.i1 = nt; u.j0 = p1; u.j1 = nt; u.k0 = p0; u.k1 = p1;
-            u.bdiag = 0; u.overwrite = 0;
-            gemm(h, u);
+        for (int I = p1 - 1; I >= p0; I--) {
+            gpx_launch_bwd_step(lmat(h), ptr<double>(h->linv), I, ptr<double>(h->work2), ptr<double>(h->alpha), h->Np, h->O,
+                                own ? 1 : 0, ncols_owned, jbase, W, W * G, max_ctas, h->st);
+            h->launches++;
+        }
+        if (own && G > 1) {
+            for (int o = 0; o < h->O; o++) {
+                double* a = ptr<double>(h->alpha) + (int64_t)o * h->Np + (int64_t)p0 * GPX_TILE;
+                GPX_NCCL(h, nccl().Broadcast(a, a, (size_t)(p1 - p0) * GPX_TILE, ncclDouble, h->rank, h->comm, h->st));
+            }
         }
     }
     return 0;
@@ -242,7 +471,7 @@ int cholesky(gpx_t* h) {
 
 extern "C" {
 
-int gpx_version(void) { return 100; }
+int gpx_version(void) { return 101; }
 
 int gpx_create(gpx_t** out, int device) {
     if (!out) return -1;
@@ -255,13 +484,16 @@ int gpx_create(gpx_t** out, int device) {
     h->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return -2; }
-    if (prop.major != 10) {
-        // sm_100a-only library: refuse loudly rather than fall back
+    if (prop.major != 10) {  // sm_100a-only library: refuse loudly rather than fall back
         delete h;
         return -5;
     }
     h->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -2; }
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->st_f, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->st_c, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return -2; }
     for (auto& e : h->ev) cudaEventCreate(&e);
     for (auto& m : h->phase_ms) m = 0.f;
     gpx_gemm_init();
@@ -275,27 +507,49 @@ void gpx_destroy(gpx_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->st);
-    DevBuf* all[] = {&h->Xs, &h->xsq, &h->ls, &h->L, &h->linv, &h->coloff, &h->linv_coloff, &h->resid, &h->work1,
-                     &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->Tt, &h->tt_coloff, &h->Xt, &h->xtsq,
-                     &h->mean_partial, &h->dmean, &h->dvar};
+    cudaStreamSynchronize(h->st_f);
+    cudaStreamSynchronize(h->st_c);
+    if (h->comm) nccl().CommDestroy(h->comm);
+    DevBuf* all[] = {&h->Xs, &h->xsq, &h->ls, &h->L, &h->linv, &h->coloff, &h->vcoloff, &h->linv_coloff, &h->resid,
+                     &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->pbuf[0], &h->pbuf[1], &h->Tt,
+                     &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar};
     for (DevBuf* b : all) release(h, *b);
-    if (h->pinned) cudaFreeHost(h->pinned);
     for (auto& e : h->ev) cudaEventDestroy(e);
     for (auto& e : h->gemm_ev) cudaEventDestroy(e);
+    for (auto& e : h->pev) cudaEventDestroy(e);
     cudaStreamDestroy(h->st);
+    cudaStreamDestroy(h->st_f);
+    cudaStreamDestroy(h->st_c);
     delete h;
 }
 
 const char* gpx_last_error(const gpx_t* h) { return h ? h->err.c_str() : "null handle"; }
 
 int gpx_comm_unique_id(char* out128) {
-    (void)out128;
-    return -6;  // multi-GPU path: see gpx_dist.cu (not linked in this build)
+    if (!out128) return -1;
+    if (!nccl().ok) return -6;
+    ncclUniqueId id;
+    if (nccl().GetUniqueId(&id) != ncclSuccess) return -7;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    memcpy(out128, &id, 128);
+    return 0;
 }
+
 int gpx_comm_init(gpx_t* h, int rank, int world, const char* uid128) {
-    (void)uid128;
-    if (world == 1 && rank == 0) return 0;
-    return fail(h, -6, "multi-GPU communicator not available in this build");
+    if (!h) return -1;
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, -1, "bad rank/world %d/%d", rank, world);
+    if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
+    h->fitted = false;
+    h->rank = rank;
+    h->world = world;
+    if (world == 1) return 0;
+    if (!uid128) return fail(h, -1, "null unique id");
+    if (!nccl().ok) return fail(h, -6, "libnccl.so.2 could not be loaded (dlopen); multi-GPU path unavailable");
+    GPX_CUDA(h, cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, uid128, 128);
+    GPX_NCCL(h, nccl().CommInitRank(&h->comm, world, id, rank));
+    return 0;
 }
 
 int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
@@ -304,6 +558,7 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "predict_batch_tiles")) { if (value < 0) return fail(h, -1, "bad predict_batch_tiles"); h->predict_batch_tiles = (int)value; return 0; }
     if (!strcmp(name, "sync_phases")) { h->sync_phases = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_timing")) { h->gemm_timing = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "lookahead")) { h->lookahead = value ? 1 : 0; return 0; }
     return fail(h, -1, "unknown option %s", name);
 }
 
@@ -317,6 +572,7 @@ int gpx_gemm_stats(gpx_t* h, double* total_ms, double* issued_flops, int64_t* la
     if (!h) return -1;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->st);
+    cudaStreamSynchronize(h->st_f);
     gemm_collect(h);
     if (total_ms) *total_ms = h->gemm_ms;
     if (issued_flops) *issued_flops = h->gemm_flops;
@@ -342,14 +598,28 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     const int64_t Np = (int64_t)nt * GPX_TILE;
     h->N = N; h->Np = Np; h->nt = nt; h->d = d; h->O = O; h->kernel_id = kernel_id; h->n_ls = n_ls;
     h->variance = variance; h->noise = noise; h->jitter = jitter; h->mean_const = mean_const;
+    h->W = h->outer_tiles < 1 ? 1 : h->outer_tiles;
+    h->npanels = (nt + h->W - 1) / h->W;
+    const int G = h->world;
     for (auto& m : h->phase_ms) m = 0.f;
 
-    // packed lower-triangular tile storage
-    const int64_t ntiles = (int64_t)nt * (nt + 1) / 2;
+    // packed lower-triangular tile storage: only the columns of the panels this rank owns
+    h->h_coloff.assign(nt, -1);
+    h->h_vcoloff.resize(nt);
+    std::vector<int64_t> lc(nt);
+    int64_t off = 0, voff = 0, max_panel = 0;
+    for (int c = 0; c < nt; c++) {
+        h->h_vcoloff[c] = voff;
+        voff += (int64_t)(nt - c) * GPX_TILE_ELEMS;
+        lc[c] = (int64_t)c * GPX_TILE_ELEMS;
+        if (panel_owner(h, c / h->W) == h->rank) { h->h_coloff[c] = off; off += (int64_t)(nt - c) * GPX_TILE_ELEMS; }
+    }
+    for (int p = 0; p < h->npanels; p++) { int64_t e = panel_elems(h, p); if (e > max_panel) max_panel = e; }
     int rc;
-    if ((rc = ensure(h, h->L, (size_t)ntiles * GPX_TILE_BYTES))) return rc;
+    if ((rc = ensure(h, h->L, (size_t)(off > 0 ? off : 1) * 8))) return rc;
     if ((rc = ensure(h, h->linv, (size_t)nt * GPX_TILE_BYTES))) return rc;
     if ((rc = ensure(h, h->coloff, (size_t)nt * 8))) return rc;
+    if ((rc = ensure(h, h->vcoloff, (size_t)nt * 8))) return rc;
     if ((rc = ensure(h, h->linv_coloff, (size_t)nt * 8))) return rc;
     if ((rc = ensure(h, h->Xs, (size_t)Np * d * 8))) return rc;
     if ((rc = ensure(h, h->xsq, (size_t)Np * 8))) return rc;
@@ -360,11 +630,12 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     if ((rc = ensure(h, h->alpha, (size_t)Np * O * 8))) return rc;
     if ((rc = ensure(h, h->scal, 64))) return rc;
     if ((rc = ensure(h, h->info, 64))) return rc;
-    h->h_coloff.resize(nt);
-    std::vector<int64_t> lc(nt);
-    int64_t off = 0;
-    for (int c = 0; c < nt; c++) { h->h_coloff[c] = off; off += (int64_t)(nt - c) * GPX_TILE_ELEMS; lc[c] = (int64_t)c * GPX_TILE_ELEMS; }
+    if (G > 1) {
+        if ((rc = ensure(h, h->pbuf[0], (size_t)max_panel * 8))) return rc;
+        if ((rc = ensure(h, h->pbuf[1], (size_t)max_panel * 8))) return rc;
+    }
     GPX_CUDA(h, cudaMemcpyAsync(h->coloff.p, h->h_coloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
+    GPX_CUDA(h, cudaMemcpyAsync(h->vcoloff.p, h->h_vcoloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
     GPX_CUDA(h, cudaMemcpyAsync(h->linv_coloff.p, lc.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
     GPX_CUDA(h, cudaMemcpyAsync(h->ls.p, lengthscale, (size_t)n_ls * 8, cudaMemcpyHostToDevice, h->st));
     GPX_CUDA(h, cudaMemsetAsync(h->info.p, 0, 64, h->st));
@@ -378,53 +649,71 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     if ((rc = to_device(h, Y, (size_t)N * O, mem, stageY, &dY))) { release(h, stageY); return rc; }
     phase_end(h, GPX_PHASE_H2D);
 
-    // K-build
+    // K-build: only the owned panels' columns
     phase_begin(h, GPX_PHASE_KBUILD);
     gpx_launch_scale_x(dX, N, Np, d, ptr<double>(h->ls), n_ls, ptr<double>(h->Xs), ptr<double>(h->xsq), h->st);
     gpx_launch_resid(dY, N, Np, O, mean_const, ptr<double>(h->resid), h->st);
-    gpx_launch_kbuild_lower(lmat(h), nt, 0, 1, nt, ptr<double>(h->Xs), ptr<double>(h->xsq), N, d, kernel_id, variance,
-                            noise + jitter, h->st);
-    h->launches += 3;
+    h->launches += 2;
+    if (G == 1) {
+        gpx_launch_kbuild_lower(lmat(h), nt, 0, 1, nt, ptr<double>(h->Xs), ptr<double>(h->xsq), N, d, kernel_id, variance,
+                                noise + jitter, h->st);
+        h->launches++;
+    } else {
+        for (int p = next_owned_panel(h, 0); p < h->npanels; p += G) {
+            gpx_launch_kbuild_lower(lmat(h), nt, panel_begin(h, p), 1, panel_end(h, p) - panel_begin(h, p), ptr<double>(h->Xs),
+                                    ptr<double>(h->xsq), N, d, kernel_id, variance, noise + jitter, h->st);
+            h->launches++;
+        }
+    }
+    GPX_CUDA(h, cudaMemcpyAsync(h->work1.p, h->resid.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, h->st));
     phase_end(h, GPX_PHASE_KBUILD);
 
-    // Cholesky
+    // Cholesky (+ fused forward substitution)
     phase_begin(h, GPX_PHASE_CHOLESKY);
-    cholesky(h);
+    rc = cholesky(h);
     phase_end(h, GPX_PHASE_CHOLESKY);
 
-    // alpha = Ky^-1 resid
-    phase_begin(h, GPX_PHASE_SOLVE);
-    GPX_CUDA(h, cudaMemcpyAsync(h->work1.p, h->resid.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, h->st));
-    const int max_ctas = 2 * h->num_sms;
-    for (int J = 0; J < nt; J++) {
-        gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, ptr<double>(h->work1), ptr<double>(h->work2), Np, O,
-                            max_ctas, h->st);
-        h->launches++;
+    // alpha: backward substitution
+    if (!rc) {
+        phase_begin(h, GPX_PHASE_SOLVE);
+        rc = backward_solve(h);
+        phase_end(h, GPX_PHASE_SOLVE);
     }
-    for (int I = nt - 1; I >= 0; I--) {
-        gpx_launch_bwd_step(lmat(h), ptr<double>(h->linv), I, ptr<double>(h->work2), ptr<double>(h->alpha), Np, O,
-                            max_ctas, h->st);
-        h->launches++;
-    }
-    phase_end(h, GPX_PHASE_SOLVE);
 
     // log-determinant and quadratic form
-    phase_begin(h, GPX_PHASE_LML);
-    gpx_launch_lml(lmat(h), nt, nullptr, ptr<double>(h->alpha), ptr<double>(h->resid), Np, O, ptr<double>(h->scal), h->st);
-    h->launches++;
-    phase_end(h, GPX_PHASE_LML);
+    if (!rc) {
+        phase_begin(h, GPX_PHASE_LML);
+        gpx_launch_lml(ptr<double>(h->linv), ptr<double>(h->alpha), ptr<double>(h->resid), Np, O, ptr<double>(h->scal), h->st);
+        h->launches++;
+        phase_end(h, GPX_PHASE_LML);
+    }
 
-    double hs[2];
+    double hs[2] = {0, 0};
     int hinfo = 0;
-    GPX_CUDA(h, cudaMemcpyAsync(hs, h->scal.p, 16, cudaMemcpyDeviceToHost, h->st));
-    GPX_CUDA(h, cudaMemcpyAsync(&hinfo, h->info.p, 4, cudaMemcpyDeviceToHost, h->st));
+    cudaMemcpyAsync(hs, h->scal.p, 16, cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(&hinfo, h->info.p, 4, cudaMemcpyDeviceToHost, h->st);
     cudaError_t e = cudaStreamSynchronize(h->st);
+    cudaError_t e2 = cudaStreamSynchronize(h->st_f);
+    cudaError_t e3 = cudaStreamSynchronize(h->st_c);
     release(h, stageY);
+    if (rc) return rc;
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) e = e3;
     if (e != cudaSuccess) return fail(h, -2, "CUDA error during fit: %s", cudaGetErrorString(e));
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, -2, "CUDA launch error during fit: %s", cudaGetErrorString(e));
     for (int ph : {GPX_PHASE_H2D, GPX_PHASE_KBUILD, GPX_PHASE_CHOLESKY, GPX_PHASE_SOLVE, GPX_PHASE_LML}) phase_collect(h, ph);
     gemm_collect(h);
+    if (G > 1) {
+        // a failed pivot is only seen by the owner of that column: agree on the smallest non-zero info
+        int* dinfo = ptr<int>(h->info);
+        int big = hinfo == 0 ? 0x7fffffff : hinfo;
+        GPX_CUDA(h, cudaMemcpyAsync(dinfo + 1, &big, 4, cudaMemcpyHostToDevice, h->st));
+        GPX_NCCL(h, nccl().AllReduce(dinfo + 1, dinfo + 1, 1, ncclInt32, ncclMin, h->comm, h->st));
+        GPX_CUDA(h, cudaMemcpyAsync(&big, dinfo + 1, 4, cudaMemcpyDeviceToHost, h->st));
+        GPX_CUDA(h, cudaStreamSynchronize(h->st));
+        hinfo = big == 0x7fffffff ? 0 : big;
+    }
     if (hinfo != 0) {
         fail(h, hinfo, "Ky is not positive definite: non-positive pivot at row %d", hinfo);
         return hinfo;
@@ -446,32 +735,57 @@ int gpx_lml(gpx_t* h, double* lml, double* logdet, double* quad) {
     return 0;
 }
 
-// variance solve for one batch of nbt test tiles held in Tt (rows = test points): Tt <- Tt L^-T, blocked.
-static void var_trsm(gpx_t* h, TileMat Tt, int nbt) {
-    const int nt = h->nt;
-    TileMat L = lmat(h), Li = linvmat(h);
-    const int W = h->outer_tiles < 1 ? 1 : h->outer_tiles;
-    for (int p0 = 0; p0 < nt; p0 += W) {
-        const int p1 = (p0 + W < nt) ? p0 + W : nt;
-        for (int k = p0; k < p1; k++) {
-            GemmJob t{};
-            t.A = Tt; t.B = Li; t.C = Tt;
-            t.tri = 0; t.i0 = 0; t.i1 = nbt; t.j0 = k; t.j1 = k + 1; t.k0 = k; t.k1 = k + 1; t.bdiag = 1; t.overwrite = 1;
-            gemm(h, t);
-            if (k + 1 < p1) {
-                GemmJob u{};
-                u.A = Tt; u.B = L; u.C = Tt;
-                u.tri = 0; u.i0 = 0; u.i1 = nbt; u.j0 = k + 1; u.j1 = p1; u.k0 = k; u.k1 = k + 1; u.bdiag = 0; u.overwrite = 0;
-                gemm(h, u);
-            }
-        }
-        if (p1 < nt) {
+// one panel step of the blocked variance solve  Tt <- Tt L^-T  for nb test tiles (rows of Tt), L operand = P
+static void var_trsm_panel(gpx_t* h, TileMat Tt, int nb, TileMat P, int p) {
+    const int nt = h->nt, p0 = panel_begin(h, p), p1 = panel_end(h, p);
+    TileMat Li = linvmat(h);
+    for (int k = p0; k < p1; k++) {
+        GemmJob t{};
+        t.A = Tt; t.B = Li; t.C = Tt;
+        t.tri = 0; t.i0 = 0; t.i1 = nb; t.ncols = 1; t.jbase = k; t.jW = GPX_JW_CONTIG; t.jstride = 0;
+        t.k0 = k; t.k1 = k + 1; t.bdiag = 1; t.overwrite = 1;
+        gemm(h, t, h->st);
+        if (k + 1 < p1) {
             GemmJob u{};
-            u.A = Tt; u.B = L; u.C = Tt;
-            u.tri = 0; u.i0 = 0; u.i1 = nbt; u.j0 = p1; u.j1 = nt; u.k0 = p0; u.k1 = p1; u.bdiag = 0; u.overwrite = 0;
-            gemm(h, u);
+            u.A = Tt; u.B = P; u.C = Tt;
+            u.tri = 0; u.i0 = 0; u.i1 = nb; u.ncols = p1 - (k + 1); u.jbase = k + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+            u.k0 = k; u.k1 = k + 1; u.bdiag = 0; u.overwrite = 0;
+            gemm(h, u, h->st);
         }
     }
+    if (p1 < nt) {
+        GemmJob u{};
+        u.A = Tt; u.B = P; u.C = Tt;
+        u.tri = 0; u.i0 = 0; u.i1 = nb; u.ncols = nt - p1; u.jbase = p1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+        u.k0 = p0; u.k1 = p1; u.bdiag = 0; u.overwrite = 0;
+        gemm(h, u, h->st);
+    }
+}
+
+// full blocked solve for one batch; world > 1 re-broadcasts the panels of L (double buffered, stream C)
+static int var_trsm(gpx_t* h, TileMat Tt, int nb) {
+    const int np = h->npanels, G = h->world;
+    if (G == 1) {
+        if (nb > 0) for (int p = 0; p < np; p++) var_trsm_panel(h, Tt, nb, lmat(h), p);
+        return 0;
+    }
+    int rc = ensure_panel_events(h, np);
+    if (rc) return rc;
+    cudaEvent_t ev_start;
+    GPX_CUDA(h, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    GPX_CUDA(h, cudaEventRecord(ev_start, h->st));
+    GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, ev_start, 0));  // previous users of the panel buffers are done
+    for (int p = 0; p < np; p++) {
+        const int q = owns_panel(h, p) ? -1 : prev_same_buffer_panel(h, p);
+        if (q >= 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, q, 2), 0));
+        if ((rc = broadcast_panel(h, p, false))) return rc;
+        GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_c));
+        GPX_CUDA(h, cudaStreamWaitEvent(h->st, pevent(h, p, 0), 0));
+        if (nb > 0) var_trsm_panel(h, Tt, nb, panel_mat(h, p), p);
+        GPX_CUDA(h, cudaEventRecord(pevent(h, p, 2), h->st));
+    }
+    cudaEventDestroy(ev_start);
+    return 0;
 }
 
 int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int include_noise, int mem) {
@@ -480,25 +794,44 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
     if (!Xs || !mean) return fail(h, -1, "null argument");
     if (Ns < 1) return fail(h, -1, "bad Ns");
     GPX_CUDA(h, cudaSetDevice(h->device));
-    const int nt = h->nt, d = h->d, O = h->O;
+    const int nt = h->nt, d = h->d, O = h->O, G = h->world;
     const int64_t Np = h->Np;
     for (int ph : {GPX_PHASE_PREDICT_KSTAR, GPX_PHASE_PREDICT_TRSM, GPX_PHASE_PREDICT_REDUCE, GPX_PHASE_H2D, GPX_PHASE_D2H}) h->phase_ms[ph] = 0.f;
 
+    // test tiles are sharded contiguously over the ranks
     const int total_tiles = (int)((Ns + GPX_TILE - 1) / GPX_TILE);
-    // batch size: a multiple of the SM count when possible, bounded by free memory when the variance is wanted
+    const int my_t0 = (int)((int64_t)total_tiles * h->rank / G), my_t1 = (int)((int64_t)total_tiles * (h->rank + 1) / G);
+    int max_shard = 0;
+    for (int r = 0; r < G; r++) {
+        int s = (int)((int64_t)total_tiles * (r + 1) / G) - (int)((int64_t)total_tiles * r / G);
+        if (s > max_shard) max_shard = s;
+    }
+    // batch size: a multiple of the SM count when possible, bounded by free memory when the variance is wanted.
+    // All ranks must agree on the number of batches (the panel broadcasts are collective), so the memory bound
+    // is the minimum over ranks.
     int cap = h->predict_batch_tiles > 0 ? h->predict_batch_tiles : h->num_sms;
     if (var) {
         size_t fr = 0, tot = 0;
         GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
         fr += h->Tt.bytes;  // reusable
+        if (G > 1) {
+            double v = (double)fr;
+            double* ds = ptr<double>(h->scal) + 4;
+            GPX_CUDA(h, cudaMemcpyAsync(ds, &v, 8, cudaMemcpyHostToDevice, h->st));
+            GPX_NCCL(h, nccl().AllReduce(ds, ds, 1, ncclDouble, ncclMin, h->comm, h->st));
+            GPX_CUDA(h, cudaMemcpyAsync(&v, ds, 8, cudaMemcpyDeviceToHost, h->st));
+            GPX_CUDA(h, cudaStreamSynchronize(h->st));
+            fr = (size_t)v;
+        }
         size_t per_tile_row = (size_t)nt * GPX_TILE_BYTES;
         size_t can = (size_t)(0.8 * (double)fr) / per_tile_row;
         if (can < 1) return fail(h, -3, "not enough device memory for the variance workspace");
         if ((size_t)cap > can) cap = (int)can;
     }
-    if (cap > total_tiles) cap = total_tiles;
-    const int nbatch = (total_tiles + cap - 1) / cap;
-    const int per = (total_tiles + nbatch - 1) / nbatch;
+    if (cap > max_shard) cap = max_shard;
+    if (cap < 1) cap = 1;
+    const int nbatch = (max_shard + cap - 1) / cap;
+    const int per = (max_shard + nbatch - 1) / nbatch;
 
     int rc;
     phase_begin(h, GPX_PHASE_H2D);
@@ -511,6 +844,10 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
         if ((rc = ensure(h, h->dmean, (size_t)Ns * O * 8))) return rc;
         dmean = ptr<double>(h->dmean);
         if (var) { if ((rc = ensure(h, h->dvar, (size_t)Ns * 8))) return rc; dvar = ptr<double>(h->dvar); }
+    }
+    if (G > 1) {  // every rank fills its rows; one all-reduce assembles the result
+        GPX_CUDA(h, cudaMemsetAsync(dmean, 0, (size_t)Ns * O * 8, h->st));
+        if (var) GPX_CUDA(h, cudaMemsetAsync(dvar, 0, (size_t)Ns * 8, h->st));
     }
     if ((rc = ensure(h, h->Xt, (size_t)per * GPX_TILE * d * 8))) return rc;
     if ((rc = ensure(h, h->xtsq, (size_t)per * GPX_TILE * 8))) return rc;
@@ -527,31 +864,33 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
     }
     const double prior_var = h->variance + (include_noise ? h->noise : 0.0);
 
-    // per-phase events only bracket the first batch exactly; accumulate by timing whole loops per phase instead:
-    // phases are interleaved per batch, so record begin at the first batch and end at the last for each phase is
-    // wrong -> time each batch's phases and accumulate on the host after a sync per batch (cheap: few batches).
     for (int b = 0; b < nbatch; b++) {
-        const int t0 = b * per;
-        const int nb = (t0 + per <= total_tiles) ? per : (total_tiles - t0);
-        if (nb <= 0) break;
+        const int t0 = my_t0 + b * per;
+        int nb = my_t1 - t0;
+        if (nb > per) nb = per;
+        if (nb < 0) nb = 0;
         const int64_t row0 = (int64_t)t0 * GPX_TILE;
-        const int64_t valid = (Ns - row0 < (int64_t)nb * GPX_TILE) ? (Ns - row0) : (int64_t)nb * GPX_TILE;
+        const int64_t valid = nb > 0 ? ((Ns - row0 < (int64_t)nb * GPX_TILE) ? (Ns - row0) : (int64_t)nb * GPX_TILE) : 0;
         phase_begin(h, GPX_PHASE_PREDICT_KSTAR);
-        gpx_launch_scale_x(dXs + row0 * d, valid, (int64_t)nb * GPX_TILE, d, ptr<double>(h->ls), h->n_ls, ptr<double>(h->Xt),
-                           ptr<double>(h->xtsq), h->st);
-        gpx_launch_kcross(Tt, nb, per, nt, ptr<double>(h->Xt), ptr<double>(h->xtsq), valid, ptr<double>(h->Xs),
-                          ptr<double>(h->xsq), h->N, d, h->kernel_id, h->variance, ptr<double>(h->alpha), O, Np,
-                          ptr<double>(h->mean_partial), h->st);
-        gpx_launch_mean_reduce(ptr<double>(h->mean_partial), per, nt, O, h->mean_const, dmean, row0, Ns, h->st);
-        h->launches += 3;
+        if (nb > 0) {
+            gpx_launch_scale_x(dXs + row0 * d, valid, (int64_t)nb * GPX_TILE, d, ptr<double>(h->ls), h->n_ls, ptr<double>(h->Xt),
+                               ptr<double>(h->xtsq), h->st);
+            gpx_launch_kcross(Tt, nb, per, nt, ptr<double>(h->Xt), ptr<double>(h->xtsq), valid, ptr<double>(h->Xs),
+                              ptr<double>(h->xsq), h->N, d, h->kernel_id, h->variance, ptr<double>(h->alpha), O, Np,
+                              ptr<double>(h->mean_partial), h->st);
+            gpx_launch_mean_reduce(ptr<double>(h->mean_partial), per, nt, O, h->mean_const, dmean, row0, row0 + valid, h->st);
+            h->launches += 3;
+        }
         phase_end(h, GPX_PHASE_PREDICT_KSTAR);
         if (var) {
             phase_begin(h, GPX_PHASE_PREDICT_TRSM);
-            var_trsm(h, Tt, nb);
+            if ((rc = var_trsm(h, Tt, nb))) return rc;
             phase_end(h, GPX_PHASE_PREDICT_TRSM);
             phase_begin(h, GPX_PHASE_PREDICT_REDUCE);
-            gpx_launch_var_reduce(Tt, nb, nt, prior_var, dvar, row0, Ns, h->st);
-            h->launches++;
+            if (nb > 0) {
+                gpx_launch_var_reduce(Tt, nb, nt, prior_var, dvar, row0, row0 + valid, h->st);
+                h->launches++;
+            }
             phase_end(h, GPX_PHASE_PREDICT_REDUCE);
         }
         if (h->sync_phases) {
@@ -564,6 +903,10 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
             }
         }
     }
+    if (G > 1) {
+        GPX_NCCL(h, nccl().AllReduce(dmean, dmean, (size_t)Ns * O, ncclDouble, ncclSum, h->comm, h->st));
+        if (var) GPX_NCCL(h, nccl().AllReduce(dvar, dvar, (size_t)Ns, ncclDouble, ncclSum, h->comm, h->st));
+    }
     if (mem == GPX_MEM_HOST) {
         phase_begin(h, GPX_PHASE_D2H);
         GPX_CUDA(h, cudaMemcpyAsync(mean, dmean, (size_t)Ns * O * 8, cudaMemcpyDeviceToHost, h->st));
@@ -571,6 +914,8 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
         phase_end(h, GPX_PHASE_D2H);
     }
     cudaError_t e = cudaStreamSynchronize(h->st);
+    cudaError_t e2 = cudaStreamSynchronize(h->st_c);
+    if (e == cudaSuccess) e = e2;
     if (e != cudaSuccess) return fail(h, -2, "CUDA error during predict: %s", cudaGetErrorString(e));
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, -2, "CUDA launch error during predict: %s", cudaGetErrorString(e));
@@ -600,6 +945,7 @@ int gpx_export(gpx_t* h, double* alpha, double* Lout) {
         if (e != cudaSuccess) return fail(h, -2, "CUDA error in gpx_export: %s", cudaGetErrorString(e));
     }
     if (Lout) {
+        if (h->world > 1) return fail(h, -1, "gpx_export: the dense factor is only available on a single-GPU handle");
         DevBuf tmp;
         if ((rc = ensure(h, tmp, (size_t)h->N * h->N * 8))) return rc;
         gpx_launch_detile(lmat(h), 1, h->N, h->N, ptr<double>(tmp), h->st);

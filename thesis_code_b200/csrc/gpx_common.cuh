@@ -66,11 +66,18 @@ struct GemmJob {
     TileMat A, B, C;
     int tri;           // 1: output tiles (I,J) with I >= J (lower triangle of a packed matrix); 0: rectangle
     int i0, i1;        // output tile rows  [i0, i1)
-    int j0, j1;        // output tile cols  [j0, j1)
+    // output tile columns: ordinal m in [0, ncols) maps to  J = jbase + (m / jW) * jstride + (m % jW)
+    // (contiguous range: jW = GPX_JW_CONTIG; block-column-cyclic shard: jW = panel width, jstride = jW * world)
+    int ncols, jbase, jW, jstride;
     int k0, k1;        // contraction tile range [k0, k1):  C(I,J) (-)= sum_k A(I,k) * B(J,k)^T
     int bdiag;         // 1: B tile index is (k, k) regardless of J (TRSM with an inverted diagonal tile)
     int overwrite;     // 1: C = +A*B^T ; 0: C -= A*B^T
+    int chunk;         // output-tile slots per CTA (set by the launcher)
 };
+#define GPX_JW_CONTIG (1 << 28)
+__host__ __device__ __forceinline__ int gpx_job_col(const GemmJob& j, int m) {
+    return j.jbase + (m / j.jW) * j.jstride + (m % j.jW);
+}
 // returns the number of (tile, k-tile) steps the launch performs (each is 2*128^3 flop); 0 if nothing was launched
 long long gpx_launch_gemm(const GemmJob& job, int num_sms, cudaStream_t st, int64_t* launch_counter);
 void gpx_gemm_init();  // sets the dynamic shared memory attribute

@@ -72,21 +72,31 @@ __global__ void __launch_bounds__(256) fwd_step_kernel(TileMat L, const double* 
     }
 }
 
-// backward step I.  z is overwritten in place by partial updates; a receives the solution.
+// backward step I.  z is updated in place for the columns this rank owns; a receives / provides the solution.
+// Owned columns below I:  J = jbase + (m / jW) * jstride + (m % jW),  m in [0, ncols)  (see GemmJob).
+// compute_alpha = 1: a_I = Linv_II^T z_I is computed here (the owner of column I; z_I is final) and published by
+// CTA 0; compute_alpha = 0: a_I was received from its owner and is only applied.
 __global__ void __launch_bounds__(256) bwd_step_kernel(TileMat L, const double* __restrict__ linv, int I,
-                                                       double* __restrict__ z, double* __restrict__ a, int64_t Np, int O) {
+                                                       double* __restrict__ z, double* __restrict__ a, int64_t Np, int O,
+                                                       int compute_alpha, int ncols, int jbase, int jW, int jstride) {
     __shared__ double sv_in[GPX_TILE], sa[GPX_TILE], scratch[GPX_TILE];
     __shared__ double part[8][GPX_TILE];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int o = 0; o < O; o++) {
         double* zo = z + (int64_t)o * Np;
-        diag_apply(linv + (int64_t)I * GPX_TILE_ELEMS, zo + (int64_t)I * GPX_TILE, true, sv_in, sa, scratch);
-        if (blockIdx.x == 0 && tid < GPX_TILE) a[(int64_t)o * Np + (int64_t)I * GPX_TILE + tid] = sa[tid];
-        for (int J = blockIdx.x; J < I; J += gridDim.x) {
+        if (compute_alpha) {
+            diag_apply(linv + (int64_t)I * GPX_TILE_ELEMS, zo + (int64_t)I * GPX_TILE, true, sv_in, sa, scratch);
+            if (blockIdx.x == 0 && tid < GPX_TILE) a[(int64_t)o * Np + (int64_t)I * GPX_TILE + tid] = sa[tid];
+        } else {
+            if (tid < GPX_TILE) sa[tid] = a[(int64_t)o * Np + (int64_t)I * GPX_TILE + tid];
+            __syncthreads();
+        }
+        for (int m = blockIdx.x; m < ncols; m += gridDim.x) {
+            const int J = jbase + (m / jW) * jstride + (m % jW);
+            if (J >= I) continue;
             const double* tp = tile_ptr(L, I, J);
-            // out[c] = sum_r L[r][c] a[r].  warp w covers rows w*16 .. w*16+15; lane -> (row pair, 16 B column pair)
-            // lane = rr*4 + t : rows w*16 + rr*2 + {0,1}?  keep it simple: each lane walks 16 rows x its 2 chunks.
-            // chunk kc (8 columns) x row i is 64 B; lane handles column pair (2*(lane&3)) of chunk set {lane>>2, (lane>>2)+8}
+            // out[c] = sum_r L[r][c] a[r]: warp w covers rows w*16..w*16+15; lane -> column pair 2*(lane&3) of the
+            // chunks {lane>>2, (lane>>2)+8}
             const int t = lane & 3, cg = lane >> 2;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -114,18 +124,18 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(TileMat L, const double* 
     }
 }
 
-// logdet = 2 sum_i log L_ii ; quad = sum alpha * resid.  One CTA, fixed order.
-__global__ void __launch_bounds__(1024) lml_kernel(TileMat L, int nt, const int* __restrict__ owned,
-                                                   const double* __restrict__ alpha, const double* __restrict__ resid,
-                                                   int64_t Np, int O, double* __restrict__ out2) {
+// logdet = 2 sum_i log L_ii = -2 sum_i log (Linv_ii)  (read from the inverted diagonal tiles, which every rank holds);
+// quad = sum alpha * resid.  One CTA, fixed order.
+__global__ void __launch_bounds__(1024) lml_kernel(const double* __restrict__ linv, const double* __restrict__ alpha,
+                                                   const double* __restrict__ resid, int64_t Np, int O,
+                                                   double* __restrict__ out2) {
     __shared__ double red[2][32];
     double ld = 0.0, q = 0.0;
     for (int64_t i = threadIdx.x; i < Np; i += blockDim.x) {
         int J = (int)(i >> 7), r = (int)(i & 127);
-        if (!owned || owned[J]) ld += log(tile_ptr(L, J, J)[gpx_tile_idx(r, r)]);
+        ld -= log(linv[(int64_t)J * GPX_TILE_ELEMS + gpx_tile_idx(r, r)]);
     }
-    if (alpha)
-        for (int64_t i = threadIdx.x; i < Np * O; i += blockDim.x) q = fma(alpha[i], resid[i], q);
+    for (int64_t i = threadIdx.x; i < Np * O; i += blockDim.x) q = fma(alpha[i], resid[i], q);
     for (int off = 16; off > 0; off >>= 1) {
         ld += __shfl_xor_sync(0xffffffffu, ld, off);
         q += __shfl_xor_sync(0xffffffffu, q, off);
@@ -166,16 +176,15 @@ void gpx_launch_fwd_step(TileMat L, const double* linv, int nt, int J, double* b
     fwd_step_kernel<<<grid, 256, 0, st>>>(L, linv, nt, J, b, z, Np, O);
 }
 
-void gpx_launch_bwd_step(TileMat L, const double* linv, int I, double* z, double* a, int64_t Np, int O, int max_ctas,
-                         cudaStream_t st) {
-    int work = I;
-    int grid = work < 1 ? 1 : (work < max_ctas ? work : max_ctas);
-    bwd_step_kernel<<<grid, 256, 0, st>>>(L, linv, I, z, a, Np, O);
+void gpx_launch_bwd_step(TileMat L, const double* linv, int I, double* z, double* a, int64_t Np, int O,
+                         int compute_alpha, int ncols, int jbase, int jW, int jstride, int max_ctas, cudaStream_t st) {
+    int grid = ncols < 1 ? 1 : (ncols < max_ctas ? ncols : max_ctas);
+    bwd_step_kernel<<<grid, 256, 0, st>>>(L, linv, I, z, a, Np, O, compute_alpha, ncols, jbase, jW, jstride);
 }
 
-void gpx_launch_lml(TileMat L, int nt, const int* owned, const double* alpha, const double* resid, int64_t Np, int O,
-                    double* out2, cudaStream_t st) {
-    lml_kernel<<<1, 1024, 0, st>>>(L, nt, owned, alpha, resid, Np, O, out2);
+void gpx_launch_lml(const double* linv, const double* alpha, const double* resid, int64_t Np, int O, double* out2,
+                    cudaStream_t st) {
+    lml_kernel<<<1, 1024, 0, st>>>(linv, alpha, resid, Np, O, out2);
 }
 
 void gpx_launch_resid(const double* Y, int64_t N, int64_t Np, int O, double mean_const, double* resid, cudaStream_t st) {
