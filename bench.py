@@ -88,22 +88,26 @@ def kernel_args(cfg):
 
 
 def cpu_oracle_step(cfg):
-    """One fit+predict of the oracle on the host; returns seconds."""
+    """One fit+predict of the oracle on the host with every host core in the BLAS pool (torchrun exports
+    OMP_NUM_THREADS=1, which would otherwise pin the baseline to one thread).  Returns (seconds, threads used)."""
     from oracle import gp_oracle as o
     kw = cfg["model"]["kwargs"]
-    t0 = time.perf_counter()
-    m = o.OracleGPModel(kernel=kw["kernel"], noise_prior=kw["noise_prior"])
-    m.init(cfg["X"], cfg["Y"])
-    m.get_statistics(cfg["Xs"], full_cov=False)
-    return time.perf_counter() - t0
-
-
-def blas_threads():
+    ncpu = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count() or 1])
+        from threadpoolctl import threadpool_info, threadpool_limits
+        ctx = threadpool_limits(limits=ncpu)
     except Exception:
-        return os.cpu_count() or 1
+        threadpool_info, ctx = None, None
+    try:
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1]) if threadpool_info else 1
+        t0 = time.perf_counter()
+        m = o.OracleGPModel(kernel=kw["kernel"], noise_prior=kw["noise_prior"])
+        m.init(cfg["X"], cfg["Y"])
+        m.get_statistics(cfg["Xs"], full_cov=False)
+        return time.perf_counter() - t0, threads
+    finally:
+        if ctx is not None:
+            ctx.restore_original_limits()
 
 
 def run_reference(args, workload, rank):
@@ -116,15 +120,16 @@ def run_reference(args, workload, rank):
     cfg = synthetic.make_config(workload, N=sN, Ns=sNs)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_oracle_step(cfg)
-    times = [cpu_oracle_step(cfg) for _ in range(args.steps)]
-    t = float(np.mean(times))
+    runs = [cpu_oracle_step(cfg) for _ in range(args.steps)]
+    t = float(np.mean([r[0] for r in runs]))
+    threads = runs[0][1]
     val = algorithmic_flops(cfg["N"], cfg["Ns"]) / t / 1e12
     sample = "%s generator at N=%d, N*=%d (bounded sample; full size is N=%s)" % (workload, cfg["N"], cfg["Ns"], {"C4": "60000", "C5": "200000"}.get(workload, "?"))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload + " (bounded CPU sample)", "N": cfg["N"], "d": cfg["d"], "N_test": cfg["Ns"]},
-            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -132,7 +137,7 @@ def run_reference(args, workload, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
@@ -145,6 +150,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = args.workload or ("C4" if args.gpus == 1 else "C5")
+    if args.steps is None:
+        # defaults that finish within minutes: C4 on one GPU is ~13 s / step, C5 (N=200k) is ~45 / 25 / 13 s on 2 / 4 / 8 GPUs
+        args.steps = 3 if args.gpus == 1 else (1 if args.gpus == 2 else 2)
 
     if args.impl == "reference":
         run_reference(args, workload, rank)
@@ -221,7 +229,7 @@ def main():
     # ---- e2e: the public GPModel API with host numpy buffers (H2D + D2H inside the timed region) ----------------
     model = GPModel.from_config(cfg["model"]["kwargs"])
     model.device = local_rank
-    model._handle = h
+    model._handle = h          # same handle: the NCCL communicator (world > 1) is already set up
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 2))
@@ -245,8 +253,11 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------
-    tensor_flops_per_step = flops * args.steps           # N^3/3 (Cholesky) + N^2 N* (variance solve): both run in the tile GEMM
-    achieved = tensor_flops_per_step / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    # N^3/3 (Cholesky) + N^2 N* (variance solve) both run in the tile GEMM; with world > 1 every rank executes 1/world
+    # of them, and rank 0's launches are the ones timed.  With look-ahead the panel GEMMs (stream F) overlap the
+    # updates (stream U), so the summed launch time can slightly exceed the step's wall time.
+    tensor_flops = flops * args.steps / max(world, 1)
+    achieved = tensor_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     chol_tflops = (float(N) ** 3 / 3) / (phases["cholesky"] * 1e-3) / 1e12
     trsm_tflops = (float(N) ** 2 * Ns) / (phases["predict_trsm"] * 1e-3) / 1e12 if phases.get("predict_trsm", 0) > 0 else None
     peaks = measured_peaks()
@@ -257,6 +268,7 @@ def main():
                                "mma.sync.m8n8k4.f64 loop measured on this pool's B200 (profiles/r01_fp64_peak.txt)",
                 "gemm_launches": gemm_launches, "gemm_ms_per_step": gemm_ms / args.steps,
                 "issued_tflops": gemm_issued / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+                "per_gpu": world > 1,
                 "kernel_share_of_step": gemm_ms / ms_total if ms_total > 0 else None}
 
     # ---- CPU baseline: oracle port on a bounded sample ------------------------------------------------------------
@@ -264,8 +276,8 @@ def main():
     if not args.no_cpu_baseline:
         sN, sNs = min(N, 12000), min(Ns, 2000)
         scfg = synthetic.make_config(workload, N=sN, Ns=sNs)
-        t = cpu_oracle_step(scfg)
-        cpu = {"value": algorithmic_flops(sN, sNs) / t / 1e12, "unit": "TFLOP/s", "cores": blas_threads(), "kind": "port",
+        t, threads = cpu_oracle_step(scfg)
+        cpu = {"value": algorithmic_flops(sN, sNs) / t / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": "port",
                "sample": "oracle (numpy/scipy port of the GPy path) on the %s generator at N=%d, N*=%d: %.1f s" % (workload, sN, sNs, t)}
 
     line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

@@ -1,0 +1,56 @@
+"""Multi-GPU parity (needs >= 2 B200s on the box; skipped otherwise): the block-column-cyclic fit + sharded predict
+must agree with the oracle and with the single-GPU path to the 1e-8 gate."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from oracle import gp_oracle as o
+from thesis_code_b200 import GPModel, synthetic
+rank = int(os.environ["RANK"]); lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+nrm = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+for cfg, N, Ns, W in [("C5", 5000, 1000, 4), ("C3", 2500, 333, 3), ("C4", 4000, 5000, 2), ("C2", 1100, 130, 1)]:
+    c = synthetic.make_config(cfg, N=N, Ns=Ns)
+    kw = c["model"]["kwargs"]
+    m = GPModel.from_config(kw); m.device = lr
+    h = m._get_handle()                      # picks the torch.distributed group up and shards the factor
+    assert h.world == dist.get_world_size()
+    h.set_option("outer_tiles", W)
+    m.init(c["X"], c["Y"])
+    mean, var = m.get_statistics(c["Xs"], full_cov=False)
+    om = o.OracleGPModel(kernel=kw["kernel"], noise_prior=kw["noise_prior"]); om.init(c["X"], c["Y"])
+    omean, ovar = om.get_statistics(c["Xs"], full_cov=False)
+    errs = (nrm(mean, omean), nrm(var, ovar), abs(m.get_marginal_log_likelihood() - om.state["lml"]) / abs(om.state["lml"]))
+    assert all(e < 1e-8 for e in errs), (cfg, errs)
+    # every rank returns the complete, identical result
+    t = torch.from_numpy(np.concatenate([mean.ravel(), var.ravel()])).cuda()
+    ref = t.clone(); dist.broadcast(ref, src=0)
+    assert bool((t == ref).all())
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_block_cyclic_two_gpus(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "OK 0" in out.stdout and "OK 1" in out.stdout

@@ -267,9 +267,21 @@ long long gpx_launch_gemm(const GemmJob& job_in, int num_sms, cudaStream_t st, i
     long long slots = count_slots(job);
     if (slots <= 0) return 0;
     // <= num_sms slots: one per CTA.  Otherwise chunks of up to 8 consecutive slots (a strip row), >= one wave of CTAs.
-    long long chunk = slots / (2LL * num_sms);
-    if (chunk < 1) chunk = 1;
-    if (chunk > 8) chunk = 8;
+    // Slots per CTA: a CTA owns `chunk` consecutive slots and retires; later CTAs are scheduled as SMs free up (this
+    // balances ragged triangular jobs and lets the panel / NCCL kernels of the other streams interleave).  Pick the
+    // chunk that minimises  rounds * (chunk * tile_time + per-CTA overhead)  -- large chunks amortise the pipeline
+    // fill, small chunks shrink the idle tail of the last round.
+    long long chunk = 1;
+    if (slots > num_sms) {
+        const double tile_us = 17.0 * (job.k1 - job.k0), ovh_us = 4.0;
+        double best = 1e300;
+        for (long long c = 1; c <= 16; c++) {
+            long long ctas = (slots + c - 1) / c;
+            long long rounds = (ctas + num_sms - 1) / num_sms;
+            double cost = (double)rounds * ((double)c * tile_us + ovh_us);
+            if (cost < best - 1e-9) { best = cost; chunk = c; }
+        }
+    }
     job.chunk = (int)chunk;
     int grid = (int)((slots + chunk - 1) / chunk);
     if (job.overwrite)
