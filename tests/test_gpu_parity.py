@@ -58,6 +58,24 @@ def test_golden_vectors_through_c_abi(gpu_handle, golden_cases):
         np.testing.assert_allclose(var2 + c["noise"], var, rtol=1e-12, atol=1e-14)
 
 
+def test_full_covariance_matches_golden_and_oracle(gpu_handle, golden_cases):
+    """full_cov=True (the reference's default for get_statistics, core_models.py:90-91,244-259)."""
+    for c in golden_cases[::3]:
+        gpu_handle.fit(c["X"], c["Y"], _gpx.KERNEL_IDS[c["kernel"]], c["variance"], c["lengthscale"], c["noise"])
+        mean, cov = gpu_handle.predict_cov(c["Xs"], include_noise=True, output_dim=c["Y"].shape[1])
+        assert normwise(mean, c["mean"]) < TOL and normwise(cov, c["cov_with_noise"]) < TOL
+        assert np.array_equal(cov, cov.T)
+    cfg = synthetic.make_config("C3", N=1500, Ns=300)
+    m, om = _fit_both(cfg)
+    mean, cov = m.get_statistics(cfg["Xs"])                      # default full_cov=True
+    omean, ocov = om.get_statistics(cfg["Xs"], full_cov=True)
+    assert mean.shape == (1, 300, 1) and cov.shape == (1, 300, 300, 1)
+    assert normwise(mean, omean) < TOL and normwise(cov, ocov) < TOL
+    mean2, var = m.get_statistics(cfg["Xs"], full_cov=False)
+    np.testing.assert_allclose(np.diagonal(cov[0, :, :, 0]), var[0, :, 0], rtol=1e-10, atol=1e-12)
+    assert np.array_equal(mean2, mean)
+
+
 def test_closed_forms_n1_n2_n3(gpu_handle):
     v, ls, s, j = 1.7, 0.8, 0.05, 1e-8
     X = np.array([[0.3]]); Y = np.array([[1.2]]); Xs = np.array([[0.9], [0.3], [5.0]])
@@ -132,8 +150,10 @@ def test_multi_output_mean_prior_and_default_noise():
     st1 = o.fit(X, Y[:, :1], "GPyMatern32", 2.0, [0.4, 0.6, 0.9], True, 1.0)
     assert m1.get_common_hyperparameters()["noise"][0] == 1.0
     assert normwise(m1.get_mean(Xs)[0], o.predict(st1, Xs)[0]) < TOL
-    with pytest.raises(AssertionError):
-        GPModel.from_config({"kernel": kern, "noise_prior": 0}).init(X, Y) if False else GPModel.from_config({"kernel": kern, "noise_prior": 0.0})._fit(X[:, :1][:0], Y)
+    # noise_prior=0 is falsy: like the reference (`if self.noise_prior:`) it is ignored and the default 1.0 is used
+    m0 = GPModel.from_config({"kernel": kern, "noise_prior": 0})
+    m0.init(X, Y[:, :1])
+    assert m0.get_common_hyperparameters()["noise"][0] == 1.0
 
 
 def test_add_observations_refits_and_pickle_roundtrip(tmp_path):

@@ -67,6 +67,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
@@ -138,6 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
                 int I, J; bool valid;
                 if (!walk.locate(job, t, I, J, valid)) break;
                 if (!valid) continue;
+                // the consumers will read-modify-write C(I,J) when they reach this tile: pull it into L2 now
+                if (!kOverwrite) bulk_prefetch_l2(tile_ptr(job.C, I, J), GPX_TILE_BYTES);
                 for (int kb = job.k0; kb < job.k1; kb++) {
                     const double* a = tile_ptr(job.A, I, kb);
                     const double* b = job.bdiag ? tile_ptr(job.B, kb, kb) : tile_ptr(job.B, J, kb);

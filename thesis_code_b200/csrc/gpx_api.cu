@@ -926,8 +926,79 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
 }
 
 int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* cov, int include_noise, int mem) {
-    (void)Xs; (void)Ns; (void)mean; (void)cov; (void)include_noise; (void)mem;
-    return fail(h, -6, "gpx_predict_cov: not implemented yet");
+    if (!h) return -1;
+    if (!h->fitted) return fail(h, -1, "gpx_predict_cov called before a successful gpx_fit");
+    if (!Xs || !mean || !cov) return fail(h, -1, "null argument");
+    if (Ns < 1) return fail(h, -1, "bad Ns");
+    GPX_CUDA(h, cudaSetDevice(h->device));
+    const int nt = h->nt, d = h->d, O = h->O;
+    const int64_t Np = h->Np;
+    const int nbt = (int)((Ns + GPX_TILE - 1) / GPX_TILE);
+    // the whole transposed cross-kernel (nbt x nt tiles) and the packed covariance must be resident at once
+    {
+        size_t fr = 0, tot = 0;
+        GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
+        fr += h->Tt.bytes;
+        double need = (double)nbt * nt * GPX_TILE_BYTES + (double)nbt * (nbt + 1) / 2 * GPX_TILE_BYTES + 3.0 * (double)Ns * Ns * 8;
+        if (need > 0.8 * (double)fr)
+            return fail(h, -3, "full predictive covariance for %lld test points needs %.1f GB of workspace; use full_cov=False",
+                        (long long)Ns, need / 1e9);
+    }
+    int rc;
+    const double* dXs;
+    if ((rc = to_device(h, Xs, (size_t)Ns * d, mem, h->stage, &dXs))) return rc;
+    DevBuf dm, dc, covt, covoff;
+    auto cleanup = [&]() { for (DevBuf* b : {&dm, &dc, &covt, &covoff}) release(h, *b); };
+    double* dmean = mean;
+    double* dcov = cov;
+    if (mem == GPX_MEM_HOST) {
+        if ((rc = ensure(h, dm, (size_t)Ns * O * 8)) || (rc = ensure(h, dc, (size_t)Ns * Ns * 8))) { cleanup(); return rc; }
+        dmean = ptr<double>(dm);
+        dcov = ptr<double>(dc);
+    }
+    std::vector<int64_t> tc(nt), cc(nbt);
+    for (int c = 0; c < nt; c++) tc[c] = (int64_t)c * nbt * GPX_TILE_ELEMS;
+    int64_t o = 0;
+    for (int c = 0; c < nbt; c++) { cc[c] = o; o += (int64_t)(nbt - c) * GPX_TILE_ELEMS; }
+    if ((rc = ensure(h, h->Xt, (size_t)nbt * GPX_TILE * d * 8)) || (rc = ensure(h, h->xtsq, (size_t)nbt * GPX_TILE * 8)) ||
+        (rc = ensure(h, h->mean_partial, (size_t)nt * nbt * GPX_TILE * O * 8)) ||
+        (rc = ensure(h, h->Tt, (size_t)nbt * nt * GPX_TILE_BYTES)) || (rc = ensure(h, h->tt_coloff, (size_t)nt * 8)) ||
+        (rc = ensure(h, covt, (size_t)o * 8)) || (rc = ensure(h, covoff, (size_t)nbt * 8))) { cleanup(); return rc; }
+    cudaMemcpyAsync(h->tt_coloff.p, tc.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st);
+    cudaMemcpyAsync(covoff.p, cc.data(), (size_t)nbt * 8, cudaMemcpyHostToDevice, h->st);
+    cudaStreamSynchronize(h->st);
+    TileMat Tt{ptr<double>(h->Tt), ptr<int64_t>(h->tt_coloff), 0};
+    TileMat Cv{ptr<double>(covt), ptr<int64_t>(covoff), 1};
+    // K(X*, X) tiles + mean;  every rank handles ALL test points here (small N*), panels of L are re-broadcast
+    gpx_launch_scale_x(dXs, Ns, (int64_t)nbt * GPX_TILE, d, ptr<double>(h->ls), h->n_ls, ptr<double>(h->Xt), ptr<double>(h->xtsq), h->st);
+    gpx_launch_kcross(Tt, nbt, nbt, nt, ptr<double>(h->Xt), ptr<double>(h->xtsq), Ns, ptr<double>(h->Xs), ptr<double>(h->xsq),
+                      h->N, d, h->kernel_id, h->variance, ptr<double>(h->alpha), O, Np, ptr<double>(h->mean_partial), h->st);
+    gpx_launch_mean_reduce(ptr<double>(h->mean_partial), nbt, nt, O, h->mean_const, dmean, 0, Ns, h->st);
+    // K(X*, X*) + noise I (exact sigma_f^2 diagonal, like kern.K(Xnew)) into packed lower tiles
+    gpx_launch_kbuild_lower(Cv, nbt, 0, 1, nbt, ptr<double>(h->Xt), ptr<double>(h->xtsq), Ns, d, h->kernel_id, h->variance,
+                            include_noise ? h->noise : 0.0, h->st);
+    h->launches += 4;
+    if ((rc = var_trsm(h, Tt, nbt))) { cleanup(); return rc; }
+    // cov -= Tt Tt^T  (lower triangle, contraction over all training tiles)
+    GemmJob g{};
+    g.A = Tt; g.B = Tt; g.C = Cv;
+    g.tri = 1; g.i0 = 0; g.i1 = nbt; g.ncols = nbt; g.jbase = 0; g.jW = GPX_JW_CONTIG; g.jstride = 0;
+    g.k0 = 0; g.k1 = nt; g.bdiag = 0; g.overwrite = 0;
+    gemm(h, g, h->st);
+    gpx_launch_detile(Cv, 2, Ns, Ns, dcov, h->st);
+    h->launches++;
+    if (mem == GPX_MEM_HOST) {
+        cudaMemcpyAsync(mean, dmean, (size_t)Ns * O * 8, cudaMemcpyDeviceToHost, h->st);
+        cudaMemcpyAsync(cov, dcov, (size_t)Ns * Ns * 8, cudaMemcpyDeviceToHost, h->st);
+    }
+    cudaError_t e = cudaStreamSynchronize(h->st);
+    cudaError_t e2 = cudaStreamSynchronize(h->st_c);
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    gemm_collect(h);
+    if (e != cudaSuccess) return fail(h, -2, "CUDA error in gpx_predict_cov: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int gpx_export(gpx_t* h, double* alpha, double* Lout) {

@@ -197,8 +197,11 @@ __global__ void detile_kernel(TileMat M, int lower, int64_t rows, int64_t cols, 
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t r = blockIdx.y;
     if (c >= cols || r >= rows) return;
+    // lower = 0: rectangular; 1: lower triangle, zeros above; 2: symmetric (mirror the stored lower triangle)
     double v = 0.0;
-    if (!lower || r >= c) v = tile_ptr(M, (int)(r >> 7), (int)(c >> 7))[gpx_tile_idx((int)(r & 127), (int)(c & 127))];
+    int64_t rr = r, cc = c;
+    if (lower == 2 && r < c) { rr = c; cc = r; }
+    if (!lower || rr >= cc) v = tile_ptr(M, (int)(rr >> 7), (int)(cc >> 7))[gpx_tile_idx((int)(rr & 127), (int)(cc & 127))];
     out[r * cols + c] = v;
 }
 
