@@ -104,7 +104,8 @@ GPX_API double gpx_phase_ms(const gpx_t* h, int phase);
 GPX_API int64_t gpx_launch_count(const gpx_t* h);
 /* Tuning knobs (tests exercise several): "outer_tiles" (tile columns per outer Cholesky panel),
  * "predict_batch_tiles" (test tiles per variance batch), "sync_phases" (1: bracket phases with events),
- * "gemm_timing" (1: per-launch events on the tile-GEMM kernel, see gpx_gemm_stats). */
+ * "gemm_timing" (1: per-launch events on the tile-GEMM kernel, see gpx_gemm_stats), "lookahead" (0: serialise the
+ * factor / communication / update streams), "gemm_max_chunk" (cap on tile slots per CTA), "trace" (see gpx_trace). */
 GPX_API int gpx_set_option(gpx_t* h, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel of this handle is launched on, so that a caller can
  * bracket calls with its own CUDA events (bench.py does, via torch.cuda.ExternalStream). */
@@ -113,6 +114,10 @@ GPX_API void* gpx_stream(const gpx_t* h);
  * (and resets) the accumulated device time in ms, the fp64 flops those launches issued (2*128^3 per tile-k step)
  * and their count.  Used for the roofline of the dominant kernel. */
 GPX_API int gpx_gemm_stats(gpx_t* h, double* total_ms, double* issued_flops, int64_t* launches);
+/* With option "trace"=1 the Cholesky records a per-panel timeline: 6 doubles per outer panel (ms since the start of
+ * the factorisation on this rank): factor start, factor end (owner only), panel ready on the update stream, next-panel
+ * update done, fused forward steps done, trailing update done.  Returns the number of values (copies up to capacity). */
+GPX_API int64_t gpx_trace(const gpx_t* h, double* out, int64_t capacity);
 /* Device-memory footprint in bytes of the current fit (factor + workspaces). */
 GPX_API int64_t gpx_bytes_allocated(const gpx_t* h);
 

@@ -58,6 +58,7 @@ SIGNATURES = {
     "gpx_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "gpx_bytes_allocated": (ctypes.c_int64, [ctypes.c_void_p]),
     "gpx_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "gpx_trace": (ctypes.c_int64, [ctypes.c_void_p, _c_double_p, ctypes.c_int64]),
     "gpx_gemm_stats": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int64)]),
 }
 
@@ -209,6 +210,14 @@ class Handle:
         ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
         self._check(self.lib.gpx_gemm_stats(self._h, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)))
         return ms.value, fl.value, n.value
+
+    def trace(self):
+        """(npanels, 6) array of per-panel timeline stamps (ms) of the last fit; needs set_option("trace", 1)."""
+        n = int(self.lib.gpx_trace(self._h, None, 0))
+        out = np.zeros(max(n, 0), dtype=np.float64)
+        if n > 0:
+            self.lib.gpx_trace(self._h, out.ctypes.data_as(_c_double_p), n)
+        return out.reshape(-1, 6)
 
     def launch_count(self):
         return int(self.lib.gpx_launch_count(self._h))

@@ -276,11 +276,12 @@ long long gpx_launch_gemm(const GemmJob& job_in, int num_sms, cudaStream_t st, i
     // balances ragged triangular jobs and lets the panel / NCCL kernels of the other streams interleave).  Pick the
     // chunk that minimises  rounds * (chunk * tile_time + per-CTA overhead)  -- large chunks amortise the pipeline
     // fill, small chunks shrink the idle tail of the last round.
+    const int max_chunk = job.chunk < 1 ? 16 : (job.chunk > 64 ? 64 : job.chunk);  // on input: the caller's cap
     long long chunk = 1;
     if (slots > num_sms) {
         const double tile_us = 17.0 * (job.k1 - job.k0), ovh_us = 4.0;
         double best = 1e300;
-        for (long long c = 1; c <= 16; c++) {
+        for (long long c = 1; c <= max_chunk; c++) {
             long long ctas = (slots + c - 1) / c;
             long long rounds = (ctas + num_sms - 1) / num_sms;
             double cost = (double)rounds * ((double)c * tile_us + ovh_us);

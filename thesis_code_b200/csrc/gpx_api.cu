@@ -66,6 +66,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;  // optional (NCCL >= 2.18)
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -88,6 +89,7 @@ NcclApi& nccl() {
     GPX_SYM(CommDestroy, "ncclCommDestroy");
     GPX_SYM(Broadcast, "ncclBroadcast");
     GPX_SYM(AllReduce, "ncclAllReduce");
+    GPX_SYM(CommSplit, "ncclCommSplit");
     GPX_SYM(GroupStart, "ncclGroupStart");
     GPX_SYM(GroupEnd, "ncclGroupEnd");
     GPX_SYM(GetErrorString, "ncclGetErrorString");
@@ -111,7 +113,9 @@ struct gpx_handle {
 
     // distribution
     int rank = 0, world = 1;
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr;     // default configuration: bandwidth-bound transfers (predict re-broadcast, all-reduce)
+    ncclComm_t comm_lo = nullptr;  // at most 4 CTAs: the panel broadcasts that overlap the trailing updates
+    int nccl_lo_ctas = 4;
 
     // options
     int outer_tiles = 4;
@@ -119,6 +123,11 @@ struct gpx_handle {
     int sync_phases = 1;
     int gemm_timing = 0;
     int lookahead = 1;
+    int gemm_max_chunk = 0;               // 0 = auto: 16 on one GPU, 4 when sharded (shorter CTAs let the panel
+                                          // factorisation and NCCL kernels of the other streams in sooner)
+    int trace = 0;                        // 1: per-panel timeline events during the Cholesky (gpx_trace)
+    std::vector<cudaEvent_t> tev;         // 6 per panel + 1 base, timing enabled
+    std::vector<float> trace_ms;          // 6 per panel: factor start, factor end, panel ready, (a) end, fwd end, (b) end
     std::vector<cudaEvent_t> gemm_ev;  // pairs, grown on demand
     size_t gemm_ev_used = 0;
     double gemm_ms = 0, gemm_flops = 0;
@@ -224,7 +233,9 @@ int to_device(gpx_t* h, const double* src, size_t count, int mem, DevBuf& stagin
 }
 
 // every DMMA tile-GEMM launch goes through here (optionally bracketed by events for the roofline numbers)
-void gemm(gpx_t* h, const GemmJob& job, cudaStream_t st) {
+void gemm(gpx_t* h, const GemmJob& job_in, cudaStream_t st) {
+    GemmJob job = job_in;
+    job.chunk = h->gemm_max_chunk > 0 ? h->gemm_max_chunk : (h->world > 1 ? 4 : 16);
     if (!h->gemm_timing) {
         long long steps = gpx_launch_gemm(job, h->num_sms, st, &h->launches);
         h->gemm_flops += 2.0 * 128 * 128 * 128 * (double)steps;
@@ -315,22 +326,32 @@ int ensure_panel_events(gpx_t* h, int npanels) {
     return 0;
 }
 
-// broadcast panel p (its packed columns and, optionally, its inverted diagonal tiles) from its owner, on stream C
+// broadcast panel p (its packed columns and, optionally, its inverted diagonal tiles) from its owner, on stream C.
+// During the factorisation (with_linv) the low-CTA communicator is used: an NCCL channel pins an SM for the whole
+// transfer and the tile GEMM needs a whole SM's shared memory, so NCCL's default ~24 channels cost the overlapped
+// trailing update ~20% on the ring's end ranks (profiles/r01_trace_4gpu.txt); 4 CTAs still move a panel in far less
+// than one update step.  The predict sweep is bandwidth-bound and uses the default communicator.
 int broadcast_panel(gpx_t* h, int p, bool with_linv) {
+    ncclComm_t comm = with_linv ? h->comm_lo : h->comm;
     const int p0 = panel_begin(h, p), p1 = panel_end(h, p), root = panel_owner(h, p);
     const int64_t elems = panel_elems(h, p);
     double* buf = owns_panel(h, p) ? ptr<double>(h->L) + h->h_coloff[p0] : recv_buf(h, p);
     GPX_NCCL(h, nccl().GroupStart());
-    ncclResult_t r1 = nccl().Broadcast(buf, buf, (size_t)elems, ncclDouble, root, h->comm, h->st_c);
+    ncclResult_t r1 = nccl().Broadcast(buf, buf, (size_t)elems, ncclDouble, root, comm, h->st_c);
     ncclResult_t r2 = ncclSuccess;
     if (with_linv) {
         double* li = ptr<double>(h->linv) + (int64_t)p0 * GPX_TILE_ELEMS;
-        r2 = nccl().Broadcast(li, li, (size_t)(p1 - p0) * GPX_TILE_ELEMS, ncclDouble, root, h->comm, h->st_c);
+        r2 = nccl().Broadcast(li, li, (size_t)(p1 - p0) * GPX_TILE_ELEMS, ncclDouble, root, comm, h->st_c);
     }
     GPX_NCCL(h, nccl().GroupEnd());
     GPX_NCCL(h, r1);
     GPX_NCCL(h, r2);
     return 0;
+}
+
+void trace_rec(gpx_t* h, int p, int which, cudaStream_t st) {
+    if (!h->trace) return;
+    cudaEventRecord(h->tev[1 + (size_t)6 * p + which], st);
 }
 
 // factor panel p in place on its owner (stream F)
@@ -365,6 +386,11 @@ int cholesky(gpx_t* h) {
     const int max_ctas = 2 * h->num_sms;
     int rc = ensure_panel_events(h, np);
     if (rc) return rc;
+    if (h->trace) {
+        while (h->tev.size() < 1 + (size_t)6 * np) { cudaEvent_t e; cudaEventCreate(&e); h->tev.push_back(e); }
+        cudaEventRecord(h->tev[0], h->st);
+        for (int p = 0; p < np; p++) for (int w = 0; w < 6; w++) cudaEventRecord(h->tev[1 + (size_t)6 * p + w], h->st);
+    }
     cudaEvent_t ev_start;  // everything enqueued on the main stream so far (K-build, residual) is done
     GPX_CUDA(h, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
     GPX_CUDA(h, cudaEventRecord(ev_start, h->st));
@@ -375,7 +401,9 @@ int cholesky(gpx_t* h) {
         const bool own = owns_panel(h, p);
         if (own) {
             if (p > 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, pevent(h, p - 1, 1), 0));
+            trace_rec(h, p, 0, h->st_f);
             factor_panel(h, p);
+            trace_rec(h, p, 1, h->st_f);
             GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_f));
             if (G > 1) {
                 GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, p, 0), 0));
@@ -389,6 +417,7 @@ int cholesky(gpx_t* h) {
         }
         // ---- stream U: consume panel p ----
         GPX_CUDA(h, cudaStreamWaitEvent(h->st, pevent(h, p, 0), 0));
+        trace_rec(h, p, 2, h->st);
         TileMat P = panel_mat(h, p);
         const int q1 = next_owned_panel(h, p + 1);
         // (a) the next panel's columns first when this rank owns them: that is what stream F waits for
@@ -402,12 +431,14 @@ int cholesky(gpx_t* h) {
             GPX_CUDA(h, cudaEventRecord(pevent(h, p, 1), h->st));
             qb = q1 + G;
         }
+        trace_rec(h, p, 3, h->st);
         // fused forward substitution with the columns of this panel (replicated right-hand side)
         for (int J = p0; J < p1; J++) {
             gpx_launch_fwd_step(P, ptr<double>(h->linv), nt, J, ptr<double>(h->work1), ptr<double>(h->work2), h->Np, h->O,
                                 max_ctas, h->st);
             h->launches++;
         }
+        trace_rec(h, p, 4, h->st);
         // (b) the rest of the owned columns
         if (qb < np) {
             GemmJob b{};
@@ -417,6 +448,7 @@ int cholesky(gpx_t* h) {
             gemm(h, b, h->st);
         }
         GPX_CUDA(h, cudaEventRecord(pevent(h, p, 2), h->st));
+        trace_rec(h, p, 5, h->st);
         if (!h->lookahead) {  // debugging aid: serialise the three streams
             GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, pevent(h, p, 2), 0));
             GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, p, 2), 0));
@@ -449,7 +481,7 @@ int backward_solve(gpx_t* h) {
         if (!own) {
             for (int o = 0; o < h->O; o++) {
                 double* a = ptr<double>(h->alpha) + (int64_t)o * h->Np + (int64_t)p0 * GPX_TILE;
-                GPX_NCCL(h, nccl().Broadcast(a, a, (size_t)(p1 - p0) * GPX_TILE, ncclDouble, panel_owner(h, p), h->comm, h->st));
+                GPX_NCCL(h, nccl().Broadcast(a, a, (size_t)(p1 - p0) * GPX_TILE, ncclDouble, panel_owner(h, p), h->comm_lo, h->st));
             }
         }
         for (int I = p1 - 1; I >= p0; I--) {
@@ -460,7 +492,7 @@ int backward_solve(gpx_t* h) {
         if (own && G > 1) {
             for (int o = 0; o < h->O; o++) {
                 double* a = ptr<double>(h->alpha) + (int64_t)o * h->Np + (int64_t)p0 * GPX_TILE;
-                GPX_NCCL(h, nccl().Broadcast(a, a, (size_t)(p1 - p0) * GPX_TILE, ncclDouble, h->rank, h->comm, h->st));
+                GPX_NCCL(h, nccl().Broadcast(a, a, (size_t)(p1 - p0) * GPX_TILE, ncclDouble, h->rank, h->comm_lo, h->st));
             }
         }
     }
@@ -509,6 +541,7 @@ void gpx_destroy(gpx_t* h) {
     cudaStreamSynchronize(h->st);
     cudaStreamSynchronize(h->st_f);
     cudaStreamSynchronize(h->st_c);
+    if (h->comm_lo && h->comm_lo != h->comm) nccl().CommDestroy(h->comm_lo);
     if (h->comm) nccl().CommDestroy(h->comm);
     DevBuf* all[] = {&h->Xs, &h->xsq, &h->ls, &h->L, &h->linv, &h->coloff, &h->vcoloff, &h->linv_coloff, &h->resid,
                      &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->pbuf[0], &h->pbuf[1], &h->Tt,
@@ -517,6 +550,7 @@ void gpx_destroy(gpx_t* h) {
     for (auto& e : h->ev) cudaEventDestroy(e);
     for (auto& e : h->gemm_ev) cudaEventDestroy(e);
     for (auto& e : h->pev) cudaEventDestroy(e);
+    for (auto& e : h->tev) cudaEventDestroy(e);
     cudaStreamDestroy(h->st);
     cudaStreamDestroy(h->st_f);
     cudaStreamDestroy(h->st_c);
@@ -538,6 +572,8 @@ int gpx_comm_unique_id(char* out128) {
 int gpx_comm_init(gpx_t* h, int rank, int world, const char* uid128) {
     if (!h) return -1;
     if (world < 1 || rank < 0 || rank >= world) return fail(h, -1, "bad rank/world %d/%d", rank, world);
+    if (h->comm_lo && h->comm_lo != h->comm) nccl().CommDestroy(h->comm_lo);
+    h->comm_lo = nullptr;
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     h->fitted = false;
     h->rank = rank;
@@ -549,6 +585,14 @@ int gpx_comm_init(gpx_t* h, int rank, int world, const char* uid128) {
     ncclUniqueId id;
     memcpy(&id, uid128, 128);
     GPX_NCCL(h, nccl().CommInitRank(&h->comm, world, id, rank));
+    h->comm_lo = h->comm;
+    if (nccl().CommSplit && h->nccl_lo_ctas > 0) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = h->nccl_lo_ctas;
+        ncclComm_t lo = nullptr;
+        if (nccl().CommSplit(h->comm, 0, rank, &lo, &cfg) == ncclSuccess && lo) h->comm_lo = lo;
+    }
     return 0;
 }
 
@@ -559,6 +603,9 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "sync_phases")) { h->sync_phases = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_timing")) { h->gemm_timing = value ? 1 : 0; return 0; }
     if (!strcmp(name, "lookahead")) { h->lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "nccl_lo_ctas")) { h->nccl_lo_ctas = (int)value; return 0; }  // takes effect at gpx_comm_init
+    if (!strcmp(name, "trace")) { h->trace = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "gemm_max_chunk")) { h->gemm_max_chunk = (int)value; return 0; }
     return fail(h, -1, "unknown option %s", name);
 }
 
@@ -581,6 +628,12 @@ int gpx_gemm_stats(gpx_t* h, double* total_ms, double* issued_flops, int64_t* la
     return 0;
 }
 int64_t gpx_bytes_allocated(const gpx_t* h) { return h ? h->bytes_alloc : -1; }
+int64_t gpx_trace(const gpx_t* h, double* out, int64_t capacity) {
+    if (!h) return -1;
+    int64_t n = (int64_t)h->trace_ms.size();
+    if (out) for (int64_t i = 0; i < n && i < capacity; i++) out[i] = h->trace_ms[i];
+    return n;
+}
 
 int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O, int kernel_id, double variance,
             const double* lengthscale, int n_ls, double noise, double jitter, double mean_const, int mem) {
@@ -704,6 +757,14 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     if (e != cudaSuccess) return fail(h, -2, "CUDA launch error during fit: %s", cudaGetErrorString(e));
     for (int ph : {GPX_PHASE_H2D, GPX_PHASE_KBUILD, GPX_PHASE_CHOLESKY, GPX_PHASE_SOLVE, GPX_PHASE_LML}) phase_collect(h, ph);
     gemm_collect(h);
+    if (h->trace) {
+        h->trace_ms.assign((size_t)6 * h->npanels, 0.f);
+        for (size_t i = 0; i < h->trace_ms.size(); i++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->tev[0], h->tev[1 + i]) == cudaSuccess) h->trace_ms[i] = ms;
+            else cudaGetLastError();
+        }
+    }
     if (G > 1) {
         // a failed pivot is only seen by the owner of that column: agree on the smallest non-zero info
         int* dinfo = ptr<int>(h->info);

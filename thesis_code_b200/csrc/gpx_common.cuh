@@ -72,7 +72,7 @@ struct GemmJob {
     int k0, k1;        // contraction tile range [k0, k1):  C(I,J) (-)= sum_k A(I,k) * B(J,k)^T
     int bdiag;         // 1: B tile index is (k, k) regardless of J (TRSM with an inverted diagonal tile)
     int overwrite;     // 1: C = +A*B^T ; 0: C -= A*B^T
-    int chunk;         // output-tile slots per CTA (set by the launcher)
+    int chunk;         // in: cap on output-tile slots per CTA (0 = default 16); the launcher overwrites it with its choice
 };
 #define GPX_JW_CONTIG (1 << 28)
 __host__ __device__ __forceinline__ int gpx_job_col(const GemmJob& j, int m) {

@@ -9,6 +9,7 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 h = _gpx.Handle(lr)
+if os.environ.get("GPX_LO_CTAS"): h.set_option("nccl_lo_ctas", int(os.environ["GPX_LO_CTAS"]))
 gdist.init_handle_comm(h, dist, rank, world)
 cases = [("C5", 5000, 1000, 4), ("C2", 3000, 700, 1), ("C3", 2500, 333, 3), ("C1", 1000, 1000, 4), ("C4", 4000, 5000, 2)]
 if len(sys.argv) > 1:
@@ -19,6 +20,9 @@ for cfg, N, Ns, W in cases:
     ls = np.atleast_1d(np.array(kk['lengthscale'], dtype=float))
     kid = _gpx.KERNEL_IDS[kw['kernel']['name']]
     h.set_option("outer_tiles", W)
+    if os.environ.get("GPX_MAX_CHUNK"): h.set_option("gemm_max_chunk", int(os.environ["GPX_MAX_CHUNK"]))
+    if os.environ.get("GPX_TRACE"): h.set_option("trace", 1)
+    if os.environ.get("GPX_LOOKAHEAD"): h.set_option("lookahead", int(os.environ["GPX_LOOKAHEAD"]))
     for rep in range(2):
         dist.barrier(); t0 = time.time()
         h.fit(c['X'], c['Y'], kid, kk.get('variance', 1.0), ls, kw['noise_prior'])
@@ -37,4 +41,7 @@ for cfg, N, Ns, W in cases:
             nrm = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
             msg += " | vs oracle: mean %.2e var %.2e lml %.2e alpha %.2e" % (nrm(mean, omean[0]), nrm(var, ovar[0, :, 0]), abs(h.lml()[0] - om.state['lml']) / abs(om.state['lml']), nrm(alpha, om.state['alpha']))
     print(msg, flush=True)
+    if os.environ.get("GPX_TRACE"):
+        tr = h.trace()
+        np.save("gpurun_out/trace_rank%d.npy" % rank, tr)
 dist.destroy_process_group()

@@ -12,6 +12,7 @@ c = synthetic.make_config(cfg, N=N, Ns=Ns)
 kw = c['model']['kwargs']; kk = kw['kernel']['kwargs']
 h = _gpx.Handle(0)
 h.set_option("outer_tiles", W)
+if os.environ.get("GPX_MAX_CHUNK"): h.set_option("gemm_max_chunk", int(os.environ["GPX_MAX_CHUNK"]))
 N, Ns = c['N'], c['Ns']
 ls = np.atleast_1d(np.array(kk['lengthscale'], dtype=float))
 kid = _gpx.KERNEL_IDS[kw['kernel']['name']]
