@@ -294,6 +294,13 @@ def main():
             "fit_predict_sec": ms_step * 1e-3, "cholesky_tflops": chol_tflops,
             "cholesky_frac_of_fp64_peak": chol_tflops / FP64_DMMA_PEAK_TFLOPS / max(world, 1),
             "variance_trsm_tflops": trsm_tflops, "phase_ms": phases,
+            # HBM-side rates of the non-tensor passes (per GPU): K-build writes 8 B per lower-triangular element once,
+            # the backward substitution reads L once (the forward pass is fused into the factorisation), the K*-build
+            # evaluates N x N* kernel entries (ALU/exp bound)
+            "kbuild_gbs": (8.0 * N * (N + 1) / 2 / max(world, 1) + 8.0 * N * d) / (phases["kbuild"] * 1e-3) / 1e9,
+            "kbuild_gevals_per_s": (N * (N + 1) / 2.0 / max(world, 1)) / (phases["kbuild"] * 1e-3) / 1e9,
+            "backward_solve_gbs": (8.0 * N * (N + 1) / 2 / max(world, 1)) / (phases["solve"] * 1e-3) / 1e9,
+            "kstar_gevals_per_s": (float(N) * Ns / max(world, 1)) / (phases["predict_kstar"] * 1e-3) / 1e9 if phases.get("predict_kstar", 0) > 0 else None,
             "hbm_peak_gbs": peaks.get("hbm_gbs"),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

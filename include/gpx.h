@@ -102,7 +102,8 @@ GPX_API int gpx_kernel_matrix(gpx_t* h, const double* X, int64_t N, int d, const
 GPX_API double gpx_phase_ms(const gpx_t* h, int phase);
 /* Kernel launches issued by this handle since creation (the `gpu_launches` claim in bench.py). */
 GPX_API int64_t gpx_launch_count(const gpx_t* h);
-/* Tuning knobs (tests exercise several): "outer_tiles" (tile columns per outer Cholesky panel),
+/* Tuning knobs (tests exercise several): "outer_tiles" (tile columns per outer Cholesky panel = ownership unit of the
+ * block-cyclic layout and K/128 of the trailing update; 0 = auto: 4 when sharded, else min(16, max(4, nt/24))),
  * "predict_batch_tiles" (test tiles per variance batch), "sync_phases" (1: bracket phases with events),
  * "gemm_timing" (1: per-launch events on the tile-GEMM kernel, see gpx_gemm_stats), "lookahead" (0: serialise the
  * factor / communication / update streams), "gemm_max_chunk" (cap on tile slots per CTA), "trace" (see gpx_trace). */

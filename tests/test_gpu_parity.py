@@ -219,7 +219,7 @@ def test_repeated_factorisations_are_bit_identical(gpu_handle):
             outs.append((alpha, mean, var, gpu_handle.lml()[0]))
         for a, mu, v, l in outs[1:]:
             assert np.array_equal(a, outs[0][0]) and np.array_equal(mu, outs[0][1]) and np.array_equal(v, outs[0][2]) and l == outs[0][3]
-    gpu_handle.set_option("outer_tiles", 4)
+    gpu_handle.set_option("outer_tiles", 0)   # back to auto
 
 
 def test_c2_full_size_vs_oracle():

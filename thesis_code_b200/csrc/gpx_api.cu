@@ -118,7 +118,7 @@ struct gpx_handle {
     int nccl_lo_ctas = 4;
 
     // options
-    int outer_tiles = 4;
+    int outer_tiles = 0;          // 0 = auto: 4 when sharded, else min(16, max(4, nt / 24)) (K of the trailing update)
     int predict_batch_tiles = 0;  // 0 = auto
     int sync_phases = 1;
     int gemm_timing = 0;
@@ -598,7 +598,7 @@ int gpx_comm_init(gpx_t* h, int rank, int world, const char* uid128) {
 
 int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!h || !name) return -1;
-    if (!strcmp(name, "outer_tiles")) { if (value < 1 || value > 64) return fail(h, -1, "outer_tiles out of range"); h->outer_tiles = (int)value; return 0; }
+    if (!strcmp(name, "outer_tiles")) { if (value < 0 || value > 64) return fail(h, -1, "outer_tiles out of range"); h->outer_tiles = (int)value; return 0; }
     if (!strcmp(name, "predict_batch_tiles")) { if (value < 0) return fail(h, -1, "bad predict_batch_tiles"); h->predict_batch_tiles = (int)value; return 0; }
     if (!strcmp(name, "sync_phases")) { h->sync_phases = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_timing")) { h->gemm_timing = value ? 1 : 0; return 0; }
@@ -651,7 +651,9 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     const int64_t Np = (int64_t)nt * GPX_TILE;
     h->N = N; h->Np = Np; h->nt = nt; h->d = d; h->O = O; h->kernel_id = kernel_id; h->n_ls = n_ls;
     h->variance = variance; h->noise = noise; h->jitter = jitter; h->mean_const = mean_const;
-    h->W = h->outer_tiles < 1 ? 1 : h->outer_tiles;
+    if (h->outer_tiles > 0) h->W = h->outer_tiles;
+    else if (h->world > 1) h->W = 4;
+    else { h->W = nt / 24; if (h->W < 4) h->W = 4; if (h->W > 16) h->W = 16; }
     h->npanels = (nt + h->W - 1) / h->W;
     const int G = h->world;
     for (auto& m : h->phase_ms) m = 0.f;
