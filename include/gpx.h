@@ -90,6 +90,14 @@ GPX_API int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, do
 GPX_API int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* cov, int include_noise,
                     int mem);
 
+/*
+ * Gradient of the log marginal likelihood of the last fit w.r.t. [variance, lengthscale (1 or d), noise, mean_const]
+ * (n_ls + 3 values; returns that count, or < 0).  Replaces the gradient GPy's optimize() evaluates each L-BFGS step when
+ * GPModel is built with do_optimize=True (src/models/core_models.py:211-223): dL_dK = 0.5 (alpha alpha^T - O Ky^-1),
+ * Ky^-1 from the tiled factor (L^-T by the DMMA triangular solve, then Y Y^T), reduced against dK/dtheta on the fly.
+ */
+GPX_API int gpx_lml_grad(gpx_t* h, double* grad, int capacity);
+
 /* Export for pickling / tests: alpha (N x O row-major) and, if L != NULL, the dense row-major lower factor
  * (N x N, upper triangle zeroed; only sensible for small N).  Host buffers. */
 GPX_API int gpx_export(gpx_t* h, double* alpha, double* L);

@@ -45,6 +45,7 @@ SIGNATURES = {
                                ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p, ctypes.c_int,
                                ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
     "gpx_lml": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p]),
+    "gpx_lml_grad": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int]),
     "gpx_predict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "gpx_predict_cov": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
@@ -174,6 +175,14 @@ class Handle:
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         self._check(self.lib.gpx_lml(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return a.value, b.value, c.value
+
+    def lml_grad(self, n_ls):
+        """d LML / d [variance, lengthscale..., noise, mean_const] of the last fit."""
+        g = np.zeros(n_ls + 3, dtype=np.float64)
+        rc = self.lib.gpx_lml_grad(self._h, g.ctypes.data_as(_c_double_p), g.size)
+        if rc < 0:
+            self._check(rc)
+        return g
 
     def export(self, N, O, want_L=False):
         alpha = np.empty((N, O), dtype=np.float64)

@@ -15,8 +15,9 @@ constant mean is ``mean(Y)`` when ``mean_prior`` is given, the predictive varian
 (``include_likelihood=True``), a fixed 1e-8 jitter is added with the noise, and a failed factorisation is retried
 with growing jitter like ``jitchol`` before raising ``LinAlgError``.
 
-Not built yet ("next" rows): hyper-parameter optimisation (``do_optimize=True``), HMC
-(``num_mcmc > 0``) and the RBF Jacobian/Hessian helpers -- they raise ``NotImplementedError`` instead of silently
+``do_optimize=True`` runs GPy's randomize + L-BFGS-B loop with the objective and its
+gradient evaluated on the GPU (``optimize.py``, ``gpx_lml_grad``).  Not built yet: HMC (``num_mcmc > 0``), GPy prior
+objects on the noise, and the RBF Jacobian/Hessian helpers -- they raise ``NotImplementedError`` instead of silently
 doing something else.
 """
 import os
@@ -159,7 +160,10 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         self._current_thetas = None
         self._handle = None
         self._fitted_theta = None
+        self._noise_fixed = False
         self.device = None
+        self.randomize_before_optimize = True   # GPModel calls gpy_model.randomize() before optimize()
+        self.max_iters = 1000                    # paramz default
 
     @classmethod
     def process_config(cls, *, kernel=None, **kwargs):
@@ -213,7 +217,7 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                     gdist.init_handle_comm(self._handle, dist)
         return self._handle
 
-    def _factorize(self):
+    def _factorize(self, retry=True):
         """K-build + Cholesky + alpha + LML on the GPU for the current parameters (jitchol-style retry)."""
         h = self._get_handle()
         X, Y = self._X, self._Y
@@ -226,6 +230,8 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                       self.noise_variance, jitter + extra, self.mean_const)
                 break
             except _gpx.NotPositiveDefiniteError:
+                if not retry:
+                    raise
                 # GPy util.linalg.jitchol: add diag.mean() * 1e-6 * 10^k for k < 5, then give up
                 tries += 1
                 if tries > 5:
@@ -243,9 +249,9 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
     def _fit(self, X, Y, Y_dir=None):
         assert X.shape[0] == Y.shape[0], \
             "X and Y has to match size. It was {} and {} respectively".format(X.shape[0], Y.shape[0])
-        if self.do_optimize:
-            raise NotImplementedError("do_optimize=True (L-BFGS / HMC hyper-parameter inference) is not built yet; "
-                                      "fix the hyper-parameters in the kernel kwargs and noise_prior")
+        if self.do_optimize and self.num_mcmc > 0:
+            raise NotImplementedError("num_mcmc > 0 (HMC over the hyper-parameters) is not built yet; use do_optimize=True "
+                                      "with num_mcmc=0 (L-BFGS) or fix the hyper-parameters")
         self.output_dim = Y.shape[-1]
         input_dim = X.shape[-1]
         first_fit = self.noise_variance is None
@@ -259,14 +265,59 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
 
         if first_fit:
             self.noise_variance = 1.0  # GPy GPRegression default likelihood variance
+            self._noise_fixed = False
             if self.noise_prior:
                 if isinstance(self.noise_prior, (float, int)):
                     assert self.noise_prior != 0, "Zero noise is ignored. Use e.g. 1e-10 instead."
                     self.noise_variance = float(self.noise_prior)
+                    self._noise_fixed = True         # Gaussian_noise.fix(noise_prior)
                 else:
-                    raise NotImplementedError("non-numeric noise priors only matter with do_optimize=True")
-        self._factorize()
+                    raise NotImplementedError("GPy prior objects on the noise variance are not supported; "
+                                              "pass a number (fixed noise) or None (free noise)")
+        if self.do_optimize:
+            self._optimize_hyperparameters()
+        else:
+            self._factorize()
         self._current_thetas = [self._param_array()]
+
+    def _optimize_hyperparameters(self):
+        """``gpy_model.randomize(); gpy_model.optimize()`` (reference core_models.py:221-223): L-BFGS-B on -LML in the
+        Logexp-transformed space, every evaluation = one GPU factorisation + one GPU gradient (gpx_lml_grad)."""
+        from . import optimize as gopt
+        nl = self.kernel.lengthscale.size
+        has_mean = self.mean_prior is not None
+        # free-parameter vector in GPy's order: [mean const, variance, lengthscales, noise (unless fixed)]
+        names = (["mean"] if has_mean else []) + ["variance"] + ["ls%d" % q for q in range(nl)] + ([] if self._noise_fixed else ["noise"])
+        positive = np.array([n != "mean" for n in names])
+
+        def unpack(theta):
+            i = 0
+            if has_mean:
+                self.mean_const = float(theta[0]); i = 1
+            self.kernel.variance = np.array([theta[i]])
+            self.kernel.lengthscale = np.array(theta[i + 1:i + 1 + nl], dtype=np.float64)
+            if not self._noise_fixed:
+                self.noise_variance = float(theta[i + 1 + nl])
+
+        def objective(theta):
+            unpack(theta)
+            self._factorize(retry=False)
+            h = self._get_handle()
+            g = h.lml_grad(nl)            # [variance, ls..., noise, mean]
+            out = ([g[nl + 2]] if has_mean else []) + [g[0]] + list(g[1:1 + nl]) + ([] if self._noise_fixed else [g[nl + 1]])
+            return h.lml()[0], np.array(out)
+
+        theta0 = np.array(([self.mean_const] if has_mean else []) + [float(self.kernel.variance[0])] +
+                          list(self.kernel.lengthscale) + ([] if self._noise_fixed else [self.noise_variance]))
+        x0 = None
+        if getattr(self, "randomize_before_optimize", True):
+            x0 = gopt.randomize(theta0.size)
+            if has_mean:
+                pass                      # GPy randomizes the mean constant too (unconstrained N(0,1) draw)
+        theta, lml, info = gopt.optimize_lbfgsb(objective, theta0, positive, x0=x0, max_iters=getattr(self, "max_iters", 1000))
+        unpack(theta)
+        self._factorize()
+        self.optimization_info = info
 
     def _predict(self, X, full_cov=True):
         num_X = X.shape[0]

@@ -49,6 +49,10 @@ void gpx_launch_lml(const double* linv, const double* alpha, const double* resid
                     cudaStream_t st);
 void gpx_launch_resid(const double* Y, int64_t N, int64_t Np, int O, double mean_const, double* resid, cudaStream_t st);
 void gpx_launch_untranspose(const double* in, int64_t N, int64_t Np, int O, double* out, cudaStream_t st);
+void gpx_launch_identity_tiles(TileMat T, int nt, cudaStream_t st);
+void gpx_launch_lml_grad(TileMat Kinv, int nt, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
+                         double variance, const double* ls, int n_ls, const double* alpha, int O, int64_t Np,
+                         double* partial, double* out, cudaStream_t st);
 
 namespace {
 
@@ -799,8 +803,10 @@ int gpx_lml(gpx_t* h, double* lml, double* logdet, double* quad) {
 }
 
 // one panel step of the blocked variance solve  Tt <- Tt L^-T  for nb test tiles (rows of Tt), L operand = P
-static void var_trsm_panel(gpx_t* h, TileMat Tt, int nb, TileMat P, int p) {
+// (upper_rows: Tt is known to be upper triangular in tile terms -- rows >= p1 are still zero -- so they are skipped)
+static void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows = false) {
     const int nt = h->nt, p0 = panel_begin(h, p), p1 = panel_end(h, p);
+    const int nb = (upper_rows && p1 < nb_in) ? p1 : nb_in;
     TileMat Li = linvmat(h);
     for (int k = p0; k < p1; k++) {
         GemmJob t{};
@@ -1062,6 +1068,70 @@ int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double
     gemm_collect(h);
     if (e != cudaSuccess) return fail(h, -2, "CUDA error in gpx_predict_cov: %s", cudaGetErrorString(e));
     return 0;
+}
+
+int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
+    if (!h) return -1;
+    if (!h->fitted) return fail(h, -1, "gpx_lml_grad called before a successful gpx_fit");
+    if (h->world > 1) return fail(h, -6, "gpx_lml_grad: only available on a single-GPU handle (not built for the sharded factor yet)");
+    const int nt = h->nt, n_ls = h->n_ls, nparam = n_ls + 3, stride = 2 + n_ls;
+    if (!grad || capacity < nparam) return fail(h, -1, "gradient buffer too small: need %d", nparam);
+    GPX_CUDA(h, cudaSetDevice(h->device));
+    // workspaces: Y = L^-T as an nt x nt tile matrix (in Tt), Ky^-1 packed lower, per-tile partial sums
+    {
+        size_t fr = 0, tot = 0;
+        GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
+        fr += h->Tt.bytes;
+        double need = ((double)nt * nt + (double)nt * (nt + 1) / 2) * GPX_TILE_BYTES;
+        if (need > 0.9 * (double)fr) return fail(h, -3, "gpx_lml_grad needs %.1f GB of workspace (N too large for one GPU)", need / 1e9);
+    }
+    int rc;
+    DevBuf kinv, kinv_off, partial, gout;
+    auto cleanup = [&]() { for (DevBuf* b : {&kinv, &kinv_off, &partial, &gout}) release(h, *b); };
+    std::vector<int64_t> tc(nt), kc(nt);
+    int64_t o = 0;
+    for (int c = 0; c < nt; c++) { tc[c] = (int64_t)c * nt * GPX_TILE_ELEMS; kc[c] = o; o += (int64_t)(nt - c) * GPX_TILE_ELEMS; }
+    if ((rc = ensure(h, h->Tt, (size_t)nt * nt * GPX_TILE_BYTES)) || (rc = ensure(h, h->tt_coloff, (size_t)nt * 8)) ||
+        (rc = ensure(h, kinv, (size_t)o * 8)) || (rc = ensure(h, kinv_off, (size_t)nt * 8)) ||
+        (rc = ensure(h, partial, (size_t)nt * nt * stride * 8)) || (rc = ensure(h, gout, (size_t)(stride + 1) * 8))) { cleanup(); return rc; }
+    cudaMemcpyAsync(h->tt_coloff.p, tc.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st);
+    cudaMemcpyAsync(kinv_off.p, kc.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st);
+    cudaStreamSynchronize(h->st);
+    TileMat Y{ptr<double>(h->Tt), ptr<int64_t>(h->tt_coloff), 0};
+    TileMat Ki{ptr<double>(kinv), ptr<int64_t>(kinv_off), 1};
+    // 1. Y = L^-T : solve Y L^T = I with the blocked DMMA solve of the variance path (upper triangular rows only)
+    gpx_launch_identity_tiles(Y, nt, h->st);
+    h->launches++;
+    for (int p = 0; p < h->npanels; p++) var_trsm_panel(h, Y, nt, lmat(h), p, true);
+    // 2. Ky^-1 = Y Y^T (lower tiles; Y(I,K) = 0 for K < I, so the contraction starts at the row group's first tile)
+    const int RG = 8;
+    for (int I0 = 0; I0 < nt; I0 += RG) {
+        const int I1 = I0 + RG < nt ? I0 + RG : nt;
+        GemmJob g{};
+        g.A = Y; g.B = Y; g.C = Ki;
+        g.tri = 1; g.i0 = I0; g.i1 = I1; g.ncols = I1; g.jbase = 0; g.jW = GPX_JW_CONTIG; g.jstride = 0;
+        g.k0 = I0; g.k1 = nt; g.bdiag = 0; g.overwrite = 1;
+        gemm(h, g, h->st);
+    }
+    // 3. dLML/dtheta = sum W .* dK/dtheta
+    gpx_launch_lml_grad(Ki, nt, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, h->d, h->kernel_id, h->variance,
+                        ptr<double>(h->ls), n_ls, ptr<double>(h->alpha), h->O, h->Np, ptr<double>(partial),
+                        ptr<double>(gout), h->st);
+    h->launches += 3;
+    std::vector<double> hg(stride + 1);
+    cudaError_t e = cudaMemcpyAsync(hg.data(), gout.p, (size_t)(stride + 1) * 8, cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    gemm_collect(h);
+    if (e != cudaSuccess) return fail(h, -2, "CUDA error in gpx_lml_grad: %s", cudaGetErrorString(e));
+    // order: [variance, lengthscale..., noise, mean_const].  The tile kernel weights diagonal elements with 1/2 and
+    // strictly-lower ones with 1 (= 2 * 1/2, symmetry), i.e. it already sums W = 0.5 (alpha alpha^T - O Kinv).
+    grad[0] = hg[0];
+    for (int q = 0; q < n_ls; q++) grad[1 + q] = hg[2 + q];
+    grad[1 + n_ls] = hg[1];
+    grad[2 + n_ls] = hg[stride];
+    return nparam;
 }
 
 int gpx_export(gpx_t* h, double* alpha, double* Lout) {

@@ -259,3 +259,189 @@ void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double*
     dim3 grid((unsigned)((cols + 255) / 256), (unsigned)rows);
     detile_kernel<<<grid, 256, 0, st>>>(M, lower, rows, cols, out);
 }
+
+// =====================================================================================================================
+// Gradient of the log marginal likelihood w.r.t. the kernel hyper-parameters (`do_optimize`).
+//   dLML/dtheta = sum_ij W_ij dK_ij/dtheta,   W = 0.5 (alpha alpha^T - O Ky^-1)      (GPy: dL_dK)
+// One CTA per lower tile (I >= J) of Ky^-1: the kernel entries and their derivatives are recomputed from the scaled
+// inputs (nothing N x N is stored besides Ky^-1), multiplied with W and reduced to 2 + n_ls partial sums per tile in a
+// fixed order (deterministic).  Off-diagonal elements count twice (symmetry).
+//   d/d variance      : K_ij / variance
+//   d/d lengthscale_q : f(r) (xs_iq - xs_jq)^2 / l_q     with xs = x / l and
+//        f = K (RBF) | 5/3 v (1 + sqrt5 r) exp(-sqrt5 r) (Matern52) | 3 v exp(-sqrt3 r) (Matern32) | v exp(-r) / r (Exponential)
+//        (isotropic: summed over q)
+//   d/d noise         : trace(W)
+// =====================================================================================================================
+namespace {
+
+__device__ __forceinline__ void gpx_k_and_f(int kernel_id, double variance, double r2, double& k, double& f) {
+    const double r = sqrt(r2);
+    if (kernel_id == 0) { k = variance * exp(-0.5 * (r * r)); f = k; }
+    else if (kernel_id == 1) {
+        const double s5 = 2.23606797749978969641;
+        const double e = exp(-s5 * r);
+        k = variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * e;
+        f = (5.0 / 3.0) * variance * (1.0 + s5 * r) * e;
+    } else if (kernel_id == 2) {
+        const double s3 = 1.73205080756887729353;
+        const double e = exp(-s3 * r);
+        k = variance * (1.0 + s3 * r) * e;
+        f = 3.0 * variance * e;
+    } else {
+        k = variance * exp(-r);
+        f = r > 0.0 ? k / r : 0.0;
+    }
+}
+
+constexpr int kMaxGradLs = kMaxD;
+
+// grid (nt, nt); partial[(I * nt + J) * stride + {0: variance, 1: noise, 2..: lengthscales}]
+__global__ void __launch_bounds__(256) lml_grad_tile_kernel(TileMat Kinv, int nt, const double* __restrict__ Xs,
+                                                            const double* __restrict__ xsq, int64_t N, int d,
+                                                            int kernel_id, double variance, const double* __restrict__ ls,
+                                                            int n_ls, const double* __restrict__ alpha, int O, int64_t Np,
+                                                            double* __restrict__ partial, int stride) {
+    extern __shared__ __align__(16) double sm[];
+    const int I = blockIdx.x, J = blockIdx.y;
+    const int tid = threadIdx.x;
+    double* out = partial + ((int64_t)I * nt + J) * stride;
+    if (I < J) return;
+    const int dp = d | 1;
+    double* sa = sm;
+    double* sb = sa + GPX_TILE * dp;
+    double* sasq = sb + GPX_TILE * dp;
+    double* sbsq = sasq + GPX_TILE;
+    double* red = sbsq + GPX_TILE;        // [8 warps][stride]
+    for (int e = tid; e < GPX_TILE * d; e += blockDim.x) {
+        int rr = e / d, k = e - rr * d;
+        sa[rr * dp + k] = Xs[((int64_t)I * GPX_TILE + rr) * d + k];
+        sb[rr * dp + k] = Xs[((int64_t)J * GPX_TILE + rr) * d + k];
+    }
+    if (tid < GPX_TILE) {
+        sasq[tid] = xsq[(int64_t)I * GPX_TILE + tid];
+        sbsq[tid] = xsq[(int64_t)J * GPX_TILE + tid];
+    }
+    __syncthreads();
+    const double* kt = tile_ptr(Kinv, I, J);
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    double gvar = 0.0, gnoise = 0.0;
+    double gls[kMaxGradLs];
+#pragma unroll 1
+    for (int q = 0; q < n_ls; q++) gls[q] = 0.0;
+    for (int rb = 0; rb < 2; rb++) {
+        const int r = warp * 16 + rb * 8 + g;
+        const int64_t gi = (int64_t)I * GPX_TILE + r;
+        for (int kc = 0; kc < 16; kc++) {
+            const double2 kinv2 = *reinterpret_cast<const double2*>(kt + kc * 1024 + r * 8 + 2 * t);
+            for (int hh = 0; hh < 2; hh++) {
+                const int c = kc * 8 + 2 * t + hh;
+                const int64_t gj = (int64_t)J * GPX_TILE + c;
+                if (gi >= N || gj >= N || gj > gi) continue;
+                double dot = 0.0;
+                for (int k = 0; k < d; k++) dot = fma(sa[r * dp + k], sb[c * dp + k], dot);
+                double r2 = fmax(-2.0 * dot + (sasq[r] + sbsq[c]), 0.0);
+                if (gi == gj) r2 = 0.0;
+                double kv, f;
+                gpx_k_and_f(kernel_id, variance, r2, kv, f);
+                double aa = 0.0;
+                for (int o = 0; o < O; o++) aa = fma(alpha[(int64_t)o * Np + gi], alpha[(int64_t)o * Np + gj], aa);
+                const double kinv = hh ? kinv2.y : kinv2.x;
+                const double w = (gi == gj ? 0.5 : 1.0) * (aa - (double)O * kinv);   // off-diagonal counted twice
+                gvar = fma(w, kv / variance, gvar);
+                if (gi == gj) gnoise += w;
+                const double wf = w * f;
+                if (n_ls == 1) {
+                    double s = 0.0;
+                    for (int k = 0; k < d; k++) { double dx = sa[r * dp + k] - sb[c * dp + k]; s = fma(dx, dx, s); }
+                    gls[0] = fma(wf, s, gls[0]);
+                } else {
+                    for (int k = 0; k < d; k++) { double dx = sa[r * dp + k] - sb[c * dp + k]; gls[k] = fma(wf, dx * dx, gls[k]); }
+                }
+            }
+        }
+    }
+    // fixed-order reduction: lanes (shuffle tree), then warps (shared memory)
+    auto wsum = [](double v) { for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off); return v; };
+    gvar = wsum(gvar);
+    gnoise = wsum(gnoise);
+    if (lane == 0) { red[warp * stride + 0] = gvar; red[warp * stride + 1] = gnoise; }
+    for (int q = 0; q < n_ls; q++) {
+        double v = wsum(gls[q]);
+        if (lane == 0) red[warp * stride + 2 + q] = v / ls[q];
+    }
+    __syncthreads();
+    if (tid < 2 + n_ls) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += red[w * stride + tid];
+        out[tid] = s;
+    }
+}
+
+// out[p] = sum over lower tiles of partial[.][p]  (fixed order)
+__global__ void lml_grad_reduce_kernel(const double* __restrict__ partial, int nt, int stride, int nparam, double* __restrict__ out) {
+    __shared__ double red[256];
+    const int p = blockIdx.x;
+    double s = 0.0;
+    for (int64_t e = threadIdx.x; e < (int64_t)nt * nt; e += blockDim.x) {
+        int I = (int)(e / nt), J = (int)(e % nt);
+        if (I >= J) s += partial[e * stride + p];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && p < nparam) out[p] = red[0];
+}
+
+// Tt <- identity (rectangular nt x nt tile matrix)
+__global__ void identity_tiles_kernel(TileMat T, int nt) {
+    const int n = blockIdx.x, J = blockIdx.y;
+    double* tp = tile_ptr(T, n, J);
+    for (int e = threadIdx.x; e < GPX_TILE_ELEMS; e += blockDim.x) {
+        int r = (e >> 3) & 127, c = (e >> 10) * 8 + (e & 7);
+        tp[e] = (n == J && r == c) ? 1.0 : 0.0;
+    }
+    gpx_publish_for_async_proxy();
+}
+
+// sum over all elements of alpha (gradient of the constant mean)
+__global__ void sum_kernel(const double* __restrict__ a, int64_t n, double* __restrict__ out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += a[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+}  // namespace
+
+void gpx_launch_identity_tiles(TileMat T, int nt, cudaStream_t st) {
+    dim3 grid(nt, nt);
+    identity_tiles_kernel<<<grid, 256, 0, st>>>(T, nt);
+}
+
+void gpx_launch_lml_grad(TileMat Kinv, int nt, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
+                         double variance, const double* ls, int n_ls, const double* alpha, int O, int64_t Np,
+                         double* partial, double* out, cudaStream_t st) {
+    const int stride = 2 + n_ls;
+    size_t smem = (size_t)(2 * GPX_TILE * (d | 1) + 2 * GPX_TILE + 8 * stride) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lml_grad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)((2 * GPX_TILE * (kMaxD | 1) + 2 * GPX_TILE + 8 * (2 + kMaxD)) * sizeof(double)));
+        attr = true;
+    }
+    dim3 grid(nt, nt);
+    lml_grad_tile_kernel<<<grid, 256, smem, st>>>(Kinv, nt, Xs, xsq, N, d, kernel_id, variance, ls, n_ls, alpha, O, Np,
+                                                  partial, stride);
+    lml_grad_reduce_kernel<<<stride, 256, 0, st>>>(partial, nt, stride, stride, out);
+    // out[stride] = sum(alpha): gradient of the constant mean
+    sum_kernel<<<1, 256, 0, st>>>(alpha, Np * O, out + stride);
+}

@@ -1,0 +1,81 @@
+"""Hyper-parameter optimisation in GPy's conventions (what ``gpy_model.randomize(); gpy_model.optimize()`` does when the
+reference builds ``GPModel`` with ``do_optimize=True``, src/models/core_models.py:211-223):
+
+* positive parameters (kernel variance, lengthscales, Gaussian noise variance) live in paramz' ``Logexp`` transformed
+  space, ``theta = log(1 + exp(x))``; the constant mean (if any) is unconstrained;
+* ``randomize()`` draws the transformed parameters from N(0, 1) with the global numpy RNG;
+* ``optimize()`` minimises ``-LML`` with scipy's L-BFGS-B (``max_iters=1000``), gradients chained through the transform.
+
+The objective is a callable ``theta -> (lml, dlml/dtheta)``; GPModel passes the GPU one (``gpx_fit`` + ``gpx_lml_grad``).
+"""
+import numpy as np
+from scipy import optimize as _sopt
+
+_LIM_VAL = 36.0
+_LOG_LIM_VAL = np.log(np.finfo(np.float64).max)
+
+
+class Logexp:
+    """paramz.transformations.Logexp"""
+
+    @staticmethod
+    def f(x):
+        x = np.asarray(x, dtype=np.float64)
+        return np.where(x > _LIM_VAL, x, np.log1p(np.exp(np.clip(x, -_LOG_LIM_VAL, _LIM_VAL))))
+
+    @staticmethod
+    def finv(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f > _LIM_VAL, f, np.log(np.expm1(f)))
+
+    @staticmethod
+    def gradfactor(f, df):
+        f = np.asarray(f, dtype=np.float64)
+        return df * np.where(f > _LIM_VAL, 1.0, -np.expm1(-f))
+
+
+def randomize(n, rand_gen=None):
+    """paramz ``randomize``: transformed parameters ~ N(0, 1) (global numpy RNG unless ``rand_gen`` is given)."""
+    rand_gen = np.random.normal if rand_gen is None else rand_gen
+    return rand_gen(size=n)
+
+
+def optimize_lbfgsb(objective, theta0, positive, x0=None, max_iters=1000, messages=False):
+    """Minimise -LML over the free parameters.
+
+    objective(theta) -> (lml, grad) with grad = dLML/dtheta (same ordering as theta);
+    positive[i] says whether theta[i] is Logexp-transformed.  ``x0``: start in transformed space (e.g. from
+    :func:`randomize`); default: the transform of ``theta0``.  Returns (theta_opt, lml_opt, info).
+    """
+    theta0 = np.asarray(theta0, dtype=np.float64)
+    positive = np.asarray(positive, dtype=bool)
+
+    def to_theta(x):
+        return np.where(positive, Logexp.f(x), x)
+
+    if x0 is None:
+        x0 = np.where(positive, Logexp.finv(np.where(positive, theta0, 1.0)), theta0)
+    evals = {"n": 0, "fails": 0}
+
+    def f_fp(x):
+        theta = to_theta(x)
+        evals["n"] += 1
+        try:
+            lml, g = objective(theta)
+        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError):
+            # paramz Model._objective_grads: swallow a few numerical failures and return a huge objective
+            evals["fails"] += 1
+            if evals["fails"] > 10:
+                raise
+            return np.inf, np.zeros_like(x)
+        g = np.asarray(g, dtype=np.float64)
+        gx = np.where(positive, Logexp.gradfactor(theta, g), g)
+        return -float(lml), -gx
+
+    res = _sopt.minimize(f_fp, np.asarray(x0, dtype=np.float64), jac=True, method="L-BFGS-B",
+                         options={"maxfun": max_iters, "maxiter": max_iters})   # scipy defaults: ftol 2.2e-9, gtol 1e-5
+    if messages:
+        print(res.message)
+    info = dict(warnflag=int(res.status), task=str(res.message), nit=int(res.nit), funcalls=int(res.nfev),
+                evaluations=evals["n"], x=res.x)
+    return to_theta(res.x), -float(res.fun), info
