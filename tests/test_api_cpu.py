@@ -110,3 +110,30 @@ def test_synthetic_configs_shapes_and_determinism():
     c = synthetic.make_config("C1")
     np.testing.assert_allclose(c["Y"], np.sin(c["X"]) / c["X"])          # Sinc (smooth.py:14-21)
     assert c["X"].min() >= -20 and c["X"].max() <= 20
+
+
+def test_normalizer_model_wraps_any_model(tmp_path):
+    """NormalizerModel (reference src/models/normalizer.py:51-158) with a stub inner model: z-scoring in, affine map out."""
+    class Stub(pkg.BaseModel):
+        def _fit(self, X, Y, Y_dir=None):
+            self.seen = (X.copy(), Y.copy())
+
+        def _get_statistics(self, X, full_cov=True):
+            mean = np.ones((1, X.shape[0], 1)) * 0.5
+            return mean, (np.ones((1, X.shape[0], X.shape[0], 1)) if full_cov else np.full((1, X.shape[0], 1), 2.0))
+    rng = np.random.RandomState(0)
+    X = rng.rand(50, 3) * 10 + 4; Y = rng.randn(50, 1) * 3 + 7
+    m = pkg.NormalizerModel(Stub())
+    m.init(X, Y)
+    Xn, Yn = m.model.seen
+    np.testing.assert_allclose(Xn.mean(0), 0, atol=1e-12); np.testing.assert_allclose(Xn.std(0), 1, rtol=1e-12)
+    np.testing.assert_allclose(Yn.mean(0), 0, atol=1e-12); np.testing.assert_allclose(Yn.std(0), 1, rtol=1e-12)
+    mean, var = m.get_statistics(X[:5], full_cov=False)
+    np.testing.assert_allclose(mean, np.full((1, 5, 1), 0.5 * Y.std(0)[0] + Y.mean(0)[0]))
+    np.testing.assert_allclose(var, np.full((1, 5, 1), 2.0 * Y.std(0)[0] ** 2))
+    mean, cov = m.get_statistics(X[:5], full_cov=True)
+    assert cov.shape == (1, 5, 5, 1, 1)                          # the reference's trailing-axis quirk is kept
+    assert m.X is X and m.Y is Y
+    nm = pkg.NormalizerModel.from_config({"model": {"name": "GPModel", "kwargs": {"kernel": {"name": "GPyRBF"}, "noise_prior": 0.1}},
+                                          "normalize_output": False})
+    assert isinstance(nm.model, pkg.GPModel) and nm._normalize_input and not nm._normalize_output

@@ -318,3 +318,23 @@ def test_do_optimize_follows_gpy_recipe():
     assert m2.noise_variance == 0.01 and m2._current_thetas[0].shape == (4,)      # [mean, variance, ls, noise]
     mean2, _ = m2.get_statistics(X[:50], full_cov=False)
     assert np.isfinite(m2.mean_const) and np.sqrt(np.mean((mean2[0] - (Y[:50] + 3.0)) ** 2)) < 0.15
+
+
+def test_normalizer_model_around_gpmodel(tmp_path):
+    """The thesis' standard stack NormalizerModel<GPModel> (notebook_header.py:17-26) vs the oracle with hand z-scoring."""
+    from thesis_code_b200 import NormalizerModel
+    rng = np.random.RandomState(3)
+    X = rng.rand(900, 4) * 50 - 10; Y = (np.sin(X[:, :1] / 7) * 20 + 100) + rng.randn(900, 1)
+    Xs = rng.rand(120, 4) * 50 - 10
+    inner = {"name": "GPModel", "kwargs": {"kernel": {"name": "GPyMatern52", "kwargs": {"lengthscale": 1.5}}, "noise_prior": 0.05}}
+    m = NormalizerModel.from_config({"model": inner})
+    m.init(X, Y)
+    mean, var = m.get_statistics(Xs, full_cov=False)
+    Xn = (X - X.mean(0)) / X.std(0); Yn = (Y - Y.mean(0)) / Y.std(0)
+    st = o.fit(Xn, Yn, "GPyMatern52", 1.0, 1.5, False, 0.05)
+    om, ov = o.predict(st, (Xs - X.mean(0)) / X.std(0))
+    assert normwise(mean[0], om * Y.std(0) + Y.mean(0)) < TOL and normwise(var[0], ov * Y.std(0) ** 2) < TOL
+    m.save(str(tmp_path / "nm"))
+    m2 = NormalizerModel.load(str(tmp_path / "nm"))
+    mean2, var2 = m2.get_statistics(Xs, full_cov=False)
+    assert np.array_equal(mean2, mean) and np.array_equal(var2, var)

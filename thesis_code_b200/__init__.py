@@ -5,6 +5,8 @@ from .kernels import GPyExponential, GPyMatern32, GPyMatern52, GPyRBF  # noqa: F
 from .core_models import (BaseModel, DerivativeGPModel, GPModel, MarginalLogLikelihoodMixin, ProbModel,  # noqa: F401
                           SaveMixin)
 
-__all__ = ["GPModel", "DerivativeGPModel", "BaseModel", "ProbModel", "SaveMixin", "MarginalLogLikelihoodMixin",
+from .normalizer import Normalizer, NormalizerModel  # noqa: F401,E402
+
+__all__ = ["Normalizer", "NormalizerModel", "GPModel", "DerivativeGPModel", "BaseModel", "ProbModel", "SaveMixin", "MarginalLogLikelihoodMixin",
            "GPyRBF", "GPyMatern52", "GPyMatern32", "GPyExponential", "ConfigMixin", "LazyConstructor",
            "construct_from_module", "lazy_construct_from_module"]
