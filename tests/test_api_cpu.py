@@ -86,9 +86,9 @@ def test_gpmodel_contract_without_gpu():
         m.add_observations(np.zeros((1, 1)), np.zeros((1, 1)))        # "Call init first"
     with pytest.raises(AssertionError):
         m._fit(np.zeros((3, 1)), np.zeros((2, 1)))                     # X/Y size mismatch
-    mo = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True, "num_mcmc": 5})
+    mo = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True, "noise_prior": object()})
     with pytest.raises(NotImplementedError):
-        mo._fit(np.zeros((3, 1)), np.zeros((3, 1)))              # HMC is not built
+        mo._fit(np.zeros((3, 1)), np.zeros((3, 1)))              # GPy prior objects on the noise are not supported
     # pickling never carries device state
     m2 = pickle.loads(pickle.dumps(m))
     assert repr(m2) == "ExactGP" and m2._handle is None

@@ -338,3 +338,21 @@ def test_normalizer_model_around_gpmodel(tmp_path):
     m2 = NormalizerModel.load(str(tmp_path / "nm"))
     mean2, var2 = m2.get_statistics(Xs, full_cov=False)
     assert np.array_equal(mean2, mean) and np.array_equal(var2, var)
+
+
+def test_hmc_hyper_posterior_gives_leading_sample_axis():
+    """num_mcmc > 0 (reference core_models.py:212-219, 249-263): T retained HMC samples, predictions (T, N*, O), each slice
+    equal to the oracle's prediction under that sample's hyper-parameters."""
+    rng = np.random.RandomState(2)
+    X = rng.rand(300, 1); Y = np.sin(6 * X) + 0.1 * rng.randn(300, 1); Xs = rng.rand(40, 1)
+    m = GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True, "num_mcmc": 3, "n_burnin": 4,
+                             "subsample_interval": 2, "step_size": 0.03, "leapfrog_steps": 4})
+    np.random.seed(7)
+    m.init(X, Y)
+    assert len(m._current_thetas) == 3 and m.has_mcmc_warmup
+    mean, var = m.get_statistics(Xs, full_cov=False)
+    assert mean.shape == (3, 40, 1) and var.shape == (3, 40, 1)
+    for i, th in enumerate(m._current_thetas):
+        st = o.fit(X, Y, "GPyRBF", th[0], th[1:2], False, th[2])
+        om, ov = o.predict(st, Xs)
+        assert normwise(mean[i], om) < TOL and normwise(var[i], ov) < TOL

@@ -162,3 +162,21 @@ def test_optimizer_driver_reaches_sklearn_optimum():
     f = gopt.Logexp.f(x)
     np.testing.assert_allclose(gopt.Logexp.finv(f)[1:], x[1:], rtol=1e-10)
     np.testing.assert_allclose(gopt.Logexp.gradfactor(f, np.ones(5))[:4], 1 / (1 + np.exp(-x[:4])), rtol=1e-9)
+
+
+def test_hmc_sampler_recipe():
+    """GPy's HMC recipe (optimize.hmc_sample) on the oracle objective: reproducible with the global numpy seed, stays in
+    the positive orthant, moves towards high marginal likelihood."""
+    from thesis_code_b200 import optimize as gopt
+    rng = np.random.RandomState(0); X = rng.rand(60, 1); Y = np.sin(6 * X) + 0.1 * rng.randn(60, 1)
+
+    def obj(th):
+        st = o.fit(X, Y, "GPyRBF", th[0], th[1:2], False, th[2]); g = o.lml_grad(st)
+        return st["lml"], g[:3]
+    np.random.seed(0)
+    s1 = gopt.hmc_sample(obj, [1., 1., 1.], [True] * 3, num_samples=24, hmc_iters=5, stepsize=0.05)
+    np.random.seed(0)
+    s2 = gopt.hmc_sample(obj, [1., 1., 1.], [True] * 3, num_samples=24, hmc_iters=5, stepsize=0.05)
+    assert s1.shape == (24, 3) and np.array_equal(s1, s2) and np.all(s1 > 0)
+    assert obj(s1[-1])[0] > obj(s1[0])[0] + 20
+    assert len(np.unique(s1[:, 0])) > 5                                            # proposals are being accepted

@@ -16,9 +16,9 @@ constant mean is ``mean(Y)`` when ``mean_prior`` is given, the predictive varian
 with growing jitter like ``jitchol`` before raising ``LinAlgError``.
 
 ``do_optimize=True`` runs GPy's randomize + L-BFGS-B loop with the objective and its
-gradient evaluated on the GPU (``optimize.py``, ``gpx_lml_grad``).  Not built yet: HMC (``num_mcmc > 0``), GPy prior
-objects on the noise, and the RBF Jacobian/Hessian helpers -- they raise ``NotImplementedError`` instead of silently
-doing something else.
+gradient evaluated on the GPU (``optimize.py``, ``gpx_lml_grad``); ``num_mcmc > 0`` runs GPy's HMC recipe on the same
+objective and predictions gain the leading hyper-sample axis.  Not built: GPy prior objects on the noise and the RBF
+Jacobian/Hessian helpers (``NotImplementedError`` instead of silently doing something else).
 """
 import os
 import pathlib
@@ -150,6 +150,7 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         self.step_size = step_size
         self.leapfrog_steps = leapfrog_steps
 
+        self.has_mcmc_warmup = False
         self.output_dim = None
         self.mean_prior = mean_prior
 
@@ -249,9 +250,6 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
     def _fit(self, X, Y, Y_dir=None):
         assert X.shape[0] == Y.shape[0], \
             "X and Y has to match size. It was {} and {} respectively".format(X.shape[0], Y.shape[0])
-        if self.do_optimize and self.num_mcmc > 0:
-            raise NotImplementedError("num_mcmc > 0 (HMC over the hyper-parameters) is not built yet; use do_optimize=True "
-                                      "with num_mcmc=0 (L-BFGS) or fix the hyper-parameters")
         self.output_dim = Y.shape[-1]
         input_dim = X.shape[-1]
         first_fit = self.noise_variance is None
@@ -274,19 +272,20 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                 else:
                     raise NotImplementedError("GPy prior objects on the noise variance are not supported; "
                                               "pass a number (fixed noise) or None (free noise)")
+        if self.do_optimize and self.num_mcmc > 0:
+            self._sample_hyperparameters()           # sets _current_thetas (one per retained HMC sample)
+            return
         if self.do_optimize:
             self._optimize_hyperparameters()
         else:
             self._factorize()
         self._current_thetas = [self._param_array()]
 
-    def _optimize_hyperparameters(self):
-        """``gpy_model.randomize(); gpy_model.optimize()`` (reference core_models.py:221-223): L-BFGS-B on -LML in the
-        Logexp-transformed space, every evaluation = one GPU factorisation + one GPU gradient (gpx_lml_grad)."""
-        from . import optimize as gopt
+    def _free_parameter_plumbing(self):
+        """(names, positive mask, unpack(theta), objective(theta) -> (lml, grad), theta0) for the free parameters in GPy's
+        order [mean const, variance, lengthscales, noise (unless fixed)]."""
         nl = self.kernel.lengthscale.size
         has_mean = self.mean_prior is not None
-        # free-parameter vector in GPy's order: [mean const, variance, lengthscales, noise (unless fixed)]
         names = (["mean"] if has_mean else []) + ["variance"] + ["ls%d" % q for q in range(nl)] + ([] if self._noise_fixed else ["noise"])
         positive = np.array([n != "mean" for n in names])
 
@@ -309,11 +308,30 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
 
         theta0 = np.array(([self.mean_const] if has_mean else []) + [float(self.kernel.variance[0])] +
                           list(self.kernel.lengthscale) + ([] if self._noise_fixed else [self.noise_variance]))
+        return names, positive, unpack, objective, theta0
+
+    def _sample_hyperparameters(self):
+        """``GPy.inference.mcmc.HMC(gpy_model, stepsize).sample(...)`` then burn-in / thinning (core_models.py:212-219).
+        The chain state persists across refits (``has_mcmc_warmup``), like the reference's ``self.hmc`` object."""
+        from . import optimize as gopt
+        assert not self._noise_fixed, "HMC samples every parameter: leave the noise free (noise_prior=None)"
+        names, positive, unpack, objective, theta0 = self._free_parameter_plumbing()
+        ss = gopt.hmc_sample(objective, theta0, positive, num_samples=self.n_burnin + self.num_mcmc * self.subsample_interval,
+                             hmc_iters=self.leapfrog_steps, stepsize=self.step_size)
+        self.has_mcmc_warmup = True
+        kept = ss[self.n_burnin::self.subsample_interval]
+        self._current_thetas = [np.array(t) for t in kept]
+        unpack(self._current_thetas[-1])
+        self._factorize()
+
+    def _optimize_hyperparameters(self):
+        """``gpy_model.randomize(); gpy_model.optimize()`` (reference core_models.py:221-223): L-BFGS-B on -LML in the
+        Logexp-transformed space, every evaluation = one GPU factorisation + one GPU gradient (gpx_lml_grad)."""
+        from . import optimize as gopt
+        names, positive, unpack, objective, theta0 = self._free_parameter_plumbing()
         x0 = None
         if getattr(self, "randomize_before_optimize", True):
-            x0 = gopt.randomize(theta0.size)
-            if has_mean:
-                pass                      # GPy randomizes the mean constant too (unconstrained N(0,1) draw)
+            x0 = gopt.randomize(theta0.size)      # GPy randomizes the mean constant too (unconstrained N(0,1) draw)
         theta, lml, info = gopt.optimize_lbfgsb(objective, theta0, positive, x0=x0, max_iters=getattr(self, "max_iters", 1000))
         unpack(theta)
         self._factorize()

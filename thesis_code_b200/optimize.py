@@ -79,3 +79,47 @@ def optimize_lbfgsb(objective, theta0, positive, x0=None, max_iters=1000, messag
     info = dict(warnflag=int(res.status), task=str(res.message), nit=int(res.nit), funcalls=int(res.nfev),
                 evaluations=evals["n"], x=res.x)
     return to_theta(res.x), -float(res.fun), info
+
+
+def hmc_sample(objective, theta0, positive, num_samples, hmc_iters=20, stepsize=1e-1):
+    """Hybrid Monte Carlo over the hyper-parameters in the transformed space, unit mass matrix -- the algorithm of
+    ``GPy.inference.mcmc.HMC(model, stepsize).sample(num_samples, hmc_iters)`` that GPModel runs when ``num_mcmc > 0``
+    (reference src/models/core_models.py:212-219).  Potential energy = -LML (no priors); each of the ``hmc_iters``
+    leapfrog steps takes two half kicks of the momentum around one full position step; Metropolis accept/reject on the
+    Hamiltonian.  Like GPy, row i records the state *before* proposal i unless the proposal is accepted.
+    Uses the global numpy RNG (np.random), as GPy does.  Returns (num_samples, n_params) constrained parameter values.
+    """
+    theta0 = np.asarray(theta0, dtype=np.float64)
+    positive = np.asarray(positive, dtype=bool)
+    n = theta0.size
+
+    def to_theta(x):
+        return np.where(positive, Logexp.f(x), x)
+
+    def energy_and_grad(x):
+        theta = to_theta(x)
+        lml, g = objective(theta)
+        gx = np.where(positive, Logexp.gradfactor(theta, np.asarray(g, dtype=np.float64)), g)
+        return -float(lml), -gx
+
+    x = np.where(positive, Logexp.finv(np.where(positive, theta0, 1.0)), theta0)
+    out = np.empty((num_samples, n))
+    const = n * np.log(2 * np.pi) / 2.0
+    for i in range(num_samples):
+        p = np.random.multivariate_normal(np.zeros(n), np.eye(n))
+        U, gU = energy_and_grad(x)
+        H_old = U + const + 0.5 * float(p @ p)
+        x_old = x.copy()
+        out[i] = to_theta(x)
+        for _ in range(hmc_iters):
+            p = p - 0.5 * stepsize * gU
+            x = x + stepsize * p
+            U, gU = energy_and_grad(x)
+            p = p - 0.5 * stepsize * gU
+        H_new = U + const + 0.5 * float(p @ p)
+        accept = 1.0 if H_old > H_new else np.exp(H_old - H_new)
+        if np.random.rand() < accept:
+            out[i] = to_theta(x)
+        else:
+            x = x_old
+    return out
