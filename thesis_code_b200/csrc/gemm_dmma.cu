@@ -8,14 +8,21 @@
 // update (A = B = factored panel), the panel TRSM (B = inverted diagonal tile) and the predictive-variance
 // triangular solve (A = transposed cross-kernel workspace, B = L).
 //
-// Structure (one persistent CTA per SM, 288 threads):
-//   * warp 8 lane 0 = producer: for every output tile and every 16-wide K slice issues two 16 KB 1-D TMA bulk
-//     copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) into a 6-stage shared-memory ring, signalled
+// Structure (TWO co-resident CTAs per SM, 160 threads each, one 64x128 HALF tile (64 rows) per work slot):
+//   * warp 4 lane 0 = producer: for every output half tile and every 16-wide K slice issues two 4 KB (A: the 64 rows
+//     of this half, one per 8-column chunk) and one 16 KB (B: 128 rows) 1-D TMA bulk copies
+//     (cp.async.bulk.shared::cluster.global, SASS UBLKCP) into a 4-stage shared-memory ring (96 KB per CTA), signalled
 //     through mbarriers (full/empty);
-//   * warps 0..7 = consumers, 2 (M) x 4 (N), each owning a 64x32 accumulator block = 8x4 DMMA 8x8 fragments held
+//   * warps 0..3 = consumers, 1 (M) x 4 (N), each owning a 64x32 accumulator block = 8x4 DMMA 8x8 fragments held
 //     in registers (64 doubles / thread).  Per 8-k chunk a warp issues 12 conflict-free LDS.128 and 64 DMMA.
-//   * accumulate mode initialises the accumulators with the old C tile (coalesced 512 B fragment loads issued
-//     while the pipeline fills) and feeds NEGATED A fragments, so the epilogue is store-only.
+//   * accumulate mode initialises the accumulators with the old C half tile (coalesced 512 B fragment loads; the
+//     producer has already pulled it into L2 with a bulk prefetch) and feeds NEGATED A fragments: store-only epilogue.
+//   * Why two small CTAs instead of one 128x128 CTA (round-1 first version): the per-tile prologue/epilogue (C load
+//     ~1.2 us, store drain + pipeline hand-over ~1.2 us, measured with tools/gemm_bench.py) left the DMMA pipe idle
+//     3% of the time at K = 4 tiles and 12% at K = 1; with two independent CTAs per SM one keeps the pipe busy while
+//     the other is between tiles (one warp per SM sub-partition already reaches 95% of the DMMA peak).
+//     The split is along ROWS so that the in-place TRSM (C = A * Linv^T written over A) stays race-free: a half only
+//     reads the A rows it overwrites.
 //
 // Roofline: FP64 tensor.  Algorithmic flops per output tile = 2 * 128^3 * (k1 - k0); measured DMMA peak on this
 // pool's B200 is 36.96 TFLOP/s (profiles/r01_fp64_peak.txt).
@@ -25,11 +32,13 @@
 
 namespace {
 
-constexpr int kStages = 6;
+constexpr int kStages = 4;
 constexpr int kStageK = 16;                              // k columns per stage
-constexpr int kOperBytes = GPX_TILE * kStageK * 8;       // 16 KB per operand per stage
-constexpr int kStageBytes = 2 * kOperBytes;              // A + B
-constexpr int kConsumerWarps = 8;
+constexpr int kOperBytes = GPX_TILE * kStageK * 8;       // B: 128 rows x 16 k = 16 KB per stage
+constexpr int kHalf = 64;                                // output rows (= A rows) per work slot
+constexpr int kAChunkBytes = kHalf * 8 * 8;              // A: 64 rows x one 8-column chunk = 4 KB
+constexpr int kStageBytes = 2 * kAChunkBytes + kOperBytes;   // 24 KB: [A chunk 0][A chunk 1][B]
+constexpr int kConsumerWarps = 4;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStages * 8 + 128;
 #ifndef GPX_WAR_FENCE_MODE
@@ -97,8 +106,10 @@ struct TileWalk {
         strip_begin = 0;
         strip_end = (long long)(i1 - strip_r0) * strip_w;
     }
-    // returns false when t is past the end; sets I,J and valid
-    __device__ bool locate(const GemmJob& j, long long t, int& I, int& J, bool& valid) {
+    // t counts HALF-tile slots: tile slot t >> 1, row half t & 1.  Returns false when t is past the end.
+    __device__ bool locate(const GemmJob& j, long long t2, int& I, int& J, int& half, bool& valid) {
+        half = (int)(t2 & 1);
+        const long long t = t2 >> 1;
         while (t >= strip_end) {
             strip_m0 += strip_w;
             if (strip_m0 >= ncols) return false;
@@ -115,7 +126,7 @@ struct TileWalk {
 };
 
 template <bool kOverwrite>
-__global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob job) {
+__global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob job) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
     uint64_t* empty = full + kStages;
@@ -138,20 +149,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
         // ---------------- producer ----------------
         if (lane == 0) {
             for (long long t = t_begin; t < t_end; t++) {
-                int I, J; bool valid;
-                if (!walk.locate(job, t, I, J, valid)) break;
+                int I, J, half; bool valid;
+                if (!walk.locate(job, t, I, J, half, valid)) break;
                 if (!valid) continue;
-                // the consumers will read-modify-write C(I,J) when they reach this tile: pull it into L2 now
-                if (!kOverwrite) bulk_prefetch_l2(tile_ptr(job.C, I, J), GPX_TILE_BYTES);
+                // the consumers will read-modify-write C(I,J) when they reach it: pull the tile into L2 now
+                if (!kOverwrite && half == 0) bulk_prefetch_l2(tile_ptr(job.C, I, J), GPX_TILE_BYTES);
                 for (int kb = job.k0; kb < job.k1; kb++) {
-                    const double* a = tile_ptr(job.A, I, kb);
+                    const double* a = tile_ptr(job.A, I, kb) + half * kHalf * 8;
                     const double* b = job.bdiag ? tile_ptr(job.B, kb, kb) : tile_ptr(job.B, J, kb);
                     for (int s = 0; s < nslice; s++) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_expect_tx(&full[stage], kStageBytes);
                         unsigned char* dst = smem + stage * kStageBytes;
-                        bulk_g2s(dst, a + s * (GPX_TILE * kStageK), kOperBytes, &full[stage]);
-                        bulk_g2s(dst + kOperBytes, b + s * (GPX_TILE * kStageK), kOperBytes, &full[stage]);
+                        // A rows [64*half, 64*half+64) of the two 8-column chunks of this K slice, then all of B's slice
+                        bulk_g2s(dst, a + s * (GPX_TILE * kStageK), kAChunkBytes, &full[stage]);
+                        bulk_g2s(dst + kAChunkBytes, a + s * (GPX_TILE * kStageK) + 1024, kAChunkBytes, &full[stage]);
+                        bulk_g2s(dst + 2 * kAChunkBytes, b + s * (GPX_TILE * kStageK), kOperBytes, &full[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -159,19 +172,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
         }
     } else {
         // ---------------- consumers ----------------
-        const int wm = warp >> 2, wn = warp & 3;
+        const int wn = warp;   // 4 warps side by side along N, each 64 rows x 32 columns
         const int g = lane >> 2, tq = lane & 3;
         // fragment offsets inside an 8-k chunk ([row][8] doubles)
-        const int a_off = (wm * 64 + g) * 8 + 2 * tq;
+        const int a_off = g * 8 + 2 * tq;
         const int b_off = (wn * 32 + g) * 8 + 2 * tq;
-        // accumulator fragment (i,j) lives at tile offset  ((wn*32 + j*8) >> 3) * 1024 + (wm*64 + i*8 + g) * 8 + 2*tq
-        const int c_off = (wn * 4) * 1024 + (wm * 64 + g) * 8 + 2 * tq;
+        // accumulator fragment (i,j) of row half h lives at tile offset  (wn*4 + j) * 1024 + (h*64 + i*8 + g) * 8 + 2*tq
+        const int c_off0 = (wn * 4) * 1024 + g * 8 + 2 * tq;
 
         for (long long t = t_begin; t < t_end; t++) {
-            int I, J; bool valid;
-            if (!walk.locate(job, t, I, J, valid)) break;
+            int I, J, half; bool valid;
+            if (!walk.locate(job, t, I, J, half, valid)) break;
             if (!valid) continue;
             double* ctile = tile_ptr(job.C, I, J);
+            const int c_off = c_off0 + half * kHalf * 8;
             double acc[8][4][2];
             if (kOverwrite) {
 #pragma unroll
@@ -191,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
                 for (int s = 0; s < nslice; s++) {
                     mbar_wait(&full[stage], phase);
                     const double* As = reinterpret_cast<const double*>(smem + stage * kStageBytes);
-                    const double* Bs = As + GPX_TILE * kStageK;
+                    const double* Bs = As + 2 * kHalf * 8;        // A: [2 chunks][64 rows][8], then B: [2 chunks][128 rows][8]
 #pragma unroll
                     for (int ch = 0; ch < kStageK / 8; ch++) {
                         double2 bf[4];
@@ -200,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_dmma_kernel(const GemmJob jo
                             bf[j] = *reinterpret_cast<const double2*>(Bs + ch * 1024 + b_off + j * 64);
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
-                            double2 af = *reinterpret_cast<const double2*>(As + ch * 1024 + a_off + i * 64);
+                            double2 af = *reinterpret_cast<const double2*>(As + ch * (kHalf * 8) + a_off + i * 64);
                             if (!kOverwrite) { af.x = -af.x; af.y = -af.y; }
 #pragma unroll
                             for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af.x, bf[j].x);
@@ -264,27 +278,30 @@ long long count_slots(const GemmJob& j) {
 void gpx_gemm_init() {
     cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    // two CTAs per SM need 2 x 96 KB of shared memory: ask for the maximum carve-out
+    cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 long long gpx_launch_gemm(const GemmJob& job_in, int num_sms, cudaStream_t st, int64_t* launch_counter) {
     GemmJob job = job_in;
     if (job.i1 <= job.i0 || job.ncols <= 0 || job.k1 <= job.k0) return 0;
-    long long slots = count_slots(job);
+    long long slots = 2 * count_slots(job);   // half-tile work slots
     if (slots <= 0) return 0;
-    // <= num_sms slots: one per CTA.  Otherwise chunks of up to 8 consecutive slots (a strip row), >= one wave of CTAs.
-    // Slots per CTA: a CTA owns `chunk` consecutive slots and retires; later CTAs are scheduled as SMs free up (this
-    // balances ragged triangular jobs and lets the panel / NCCL kernels of the other streams interleave).  Pick the
-    // chunk that minimises  rounds * (chunk * tile_time + per-CTA overhead)  -- large chunks amortise the pipeline
-    // fill, small chunks shrink the idle tail of the last round.
-    const int max_chunk = job.chunk < 1 ? 16 : (job.chunk > 64 ? 64 : job.chunk);  // on input: the caller's cap
+    // Slots per CTA: a CTA owns `chunk` consecutive half-tile slots and retires; later CTAs are scheduled as SMs free
+    // up (this balances ragged triangular jobs and lets the panel / NCCL kernels of the other streams interleave).
+    // Two CTAs are resident per SM.  Pick the chunk that minimises  rounds * (chunk * slot_time + per-CTA overhead):
+    // large chunks amortise the pipeline fill, small chunks shrink the idle tail of the last round.
+    const int resident = 2 * num_sms;
+    const int max_chunk = 2 * (job.chunk < 1 ? 16 : (job.chunk > 64 ? 64 : job.chunk));  // caller's cap is in full tiles
     long long chunk = 1;
-    if (slots > num_sms) {
-        const double tile_us = 17.0 * (job.k1 - job.k0), ovh_us = 4.0;
+    if (slots > resident) {
+        const double slot_us = 17.0 * (job.k1 - job.k0), ovh_us = 4.0;   // a half tile at half an SM's rate
         double best = 1e300;
         for (long long c = 1; c <= max_chunk; c++) {
             long long ctas = (slots + c - 1) / c;
-            long long rounds = (ctas + num_sms - 1) / num_sms;
-            double cost = (double)rounds * ((double)c * tile_us + ovh_us);
+            long long rounds = (ctas + resident - 1) / resident;
+            double cost = (double)rounds * ((double)c * slot_us + ovh_us);
             if (cost < best - 1e-9) { best = cost; chunk = c; }
         }
     }

@@ -1134,6 +1134,43 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     return nparam;
 }
 
+// Development aid (tools/gemm_bench.py): time the tile GEMM in isolation on a synthetic rectangular tile matrix.
+// C (rows x cols tiles) (-)= A (rows x ktiles) * B (cols x ktiles)^T, `reps` launches; returns the mean ms per launch.
+GPX_API double gpx_debug_gemm(gpx_t* h, int rows, int cols, int ktiles, int overwrite, int max_chunk, int reps) {
+    if (!h || rows < 1 || cols < 1 || ktiles < 1) return -1.0;
+    cudaSetDevice(h->device);
+    const int ncolsA = ktiles, ncolsC = cols;
+    DevBuf A, B, C, offA, offB, offC;
+    size_t tb = GPX_TILE_BYTES;
+    if (ensure(h, A, (size_t)rows * ktiles * tb) || ensure(h, B, (size_t)cols * ktiles * tb) || ensure(h, C, (size_t)rows * cols * tb) ||
+        ensure(h, offA, (size_t)ncolsA * 8) || ensure(h, offB, (size_t)ktiles * 8) || ensure(h, offC, (size_t)ncolsC * 8)) return -2.0;
+    std::vector<int64_t> oa(ktiles), ob(ktiles), oc(cols);
+    for (int k = 0; k < ktiles; k++) { oa[k] = (int64_t)k * rows * GPX_TILE_ELEMS; ob[k] = (int64_t)k * cols * GPX_TILE_ELEMS; }
+    for (int c = 0; c < cols; c++) oc[c] = (int64_t)c * rows * GPX_TILE_ELEMS;
+    cudaMemcpy(offA.p, oa.data(), (size_t)ktiles * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(offB.p, ob.data(), (size_t)ktiles * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(offC.p, oc.data(), (size_t)cols * 8, cudaMemcpyHostToDevice);
+    cudaMemset(A.p, 0, A.bytes); cudaMemset(B.p, 0, B.bytes); cudaMemset(C.p, 0, C.bytes);
+    GemmJob g{};
+    g.A = TileMat{ptr<double>(A), ptr<int64_t>(offA), 0};
+    g.B = TileMat{ptr<double>(B), ptr<int64_t>(offB), 0};
+    g.C = TileMat{ptr<double>(C), ptr<int64_t>(offC), 0};
+    g.tri = 0; g.i0 = 0; g.i1 = rows; g.ncols = cols; g.jbase = 0; g.jW = GPX_JW_CONTIG; g.jstride = 0;
+    g.k0 = 0; g.k1 = ktiles; g.bdiag = 0; g.overwrite = overwrite; g.chunk = max_chunk;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    gpx_launch_gemm(g, h->num_sms, h->st, nullptr);
+    cudaEventRecord(e0, h->st);
+    for (int r = 0; r < reps; r++) gpx_launch_gemm(g, h->num_sms, h->st, nullptr);
+    cudaEventRecord(e1, h->st);
+    cudaStreamSynchronize(h->st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (DevBuf* b : {&A, &B, &C, &offA, &offB, &offC}) release(h, *b);
+    return cudaGetLastError() == cudaSuccess ? ms / reps : -3.0;
+}
+
 int gpx_export(gpx_t* h, double* alpha, double* Lout) {
     if (!h) return -1;
     if (!h->fitted) return fail(h, -1, "gpx_export called before a successful gpx_fit");

@@ -1,0 +1,15 @@
+"""Isolated timing of the DMMA tile GEMM (gpx_debug_gemm, a development-only symbol that is not part of include/gpx.h)."""
+import ctypes, sys
+sys.path.insert(0, '.')
+from thesis_code_b200 import _gpx
+h = _gpx.Handle(0)
+f = h.lib.gpx_debug_gemm
+f.restype = ctypes.c_double
+f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+print("rows cols K overwrite chunk :   ms    TFLOP/s")
+for (rows, cols, K, ow, ch) in [(148, 64, 1, 0, 16), (148, 64, 2, 0, 16), (148, 64, 4, 0, 16), (148, 64, 8, 0, 16), (148, 64, 16, 0, 16),
+                                (148, 64, 4, 1, 16), (148, 64, 1, 1, 16), (148, 64, 4, 0, 1), (148, 64, 4, 0, 4), (148, 64, 4, 0, 64),
+                                (148, 8, 4, 0, 8), (148, 1, 4, 0, 1), (148, 1, 16, 0, 1), (148, 1, 64, 0, 1), (296, 1, 64, 0, 1)]:
+    ms = f(h._h, rows, cols, K, ow, ch, 5)
+    fl = 2.0 * 128 ** 3 * rows * cols * K
+    print("%4d %4d %3d %d %3d : %8.3f  %6.2f" % (rows, cols, K, ow, ch, ms, fl / ms / 1e9))
