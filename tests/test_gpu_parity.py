@@ -27,7 +27,7 @@ def _fit_both(c, h=None, **opts):
 
 
 @pytest.mark.parametrize("name", ["GPyRBF", "GPyMatern52", "GPyMatern32", "GPyExponential"])
-@pytest.mark.parametrize("N,M,d,ARD", [(1, 1, 1, False), (127, 3, 2, True), (128, 129, 1, False), (300, 77, 3, True), (1000, 500, 8, True), (515, 260, 33, True)])
+@pytest.mark.parametrize("N,M,d,ARD", [(1, 1, 1, False), (127, 3, 2, True), (128, 129, 1, False), (300, 77, 3, True), (1000, 500, 8, True), (515, 260, 33, True), (260, 131, 64, True), (200, 140, 150, True)])
 def test_kernel_build_matches_oracle(gpu_handle, name, N, M, d, ARD):
     rng = np.random.RandomState(N + d)
     X = rng.rand(N, d) * 3
@@ -199,8 +199,9 @@ def test_bad_arguments_fail_loudly(gpu_handle):
         gpu_handle.fit(X, Y, 0, 1.0, [1.0, 2.0, 3.0], 0.1)     # wrong lengthscale count
     with pytest.raises(_gpx.GpxError):
         gpu_handle.fit(X, Y, 0, -1.0, [1.0], 0.1)              # negative variance
+    gpu_handle.fit(np.random.rand(10, 65), Y, 0, 1.0, [1.0], 0.1)       # any input dimension is accepted (chunked K-build)
     with pytest.raises(_gpx.GpxError):
-        gpu_handle.fit(np.random.rand(10, 65), Y, 0, 1.0, [1.0], 0.1)   # d above the supported maximum
+        gpu_handle.lml_grad(1)                                         # ... but the gradient kernel is limited to d <= 64
 
 
 def test_repeated_factorisations_are_bit_identical(gpu_handle):

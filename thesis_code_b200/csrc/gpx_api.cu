@@ -34,6 +34,7 @@
 // launchers from the other translation units
 void gpx_kbuild_init();
 int gpx_kbuild_max_d();
+int gpx_grad_max_d();
 void gpx_launch_kbuild_lower(TileMat L, int nt, int jfirst, int jstep, int ncols, const double* Xs, const double* xsq,
                              int64_t N, int d, int kernel_id, double variance, double diag_add, cudaStream_t st);
 void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, double mean_const, double* mean,
@@ -1076,6 +1077,7 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     if (h->world > 1) return fail(h, -6, "gpx_lml_grad: only available on a single-GPU handle (not built for the sharded factor yet)");
     const int nt = h->nt, n_ls = h->n_ls, nparam = n_ls + 3, stride = 2 + n_ls;
     if (!grad || capacity < nparam) return fail(h, -1, "gradient buffer too small: need %d", nparam);
+    if (h->d > gpx_grad_max_d()) return fail(h, -1, "gpx_lml_grad supports input dimension <= %d", gpx_grad_max_d());
     GPX_CUDA(h, cudaSetDevice(h->device));
     // workspaces: Y = L^-T as an nt x nt tile matrix (in Tt), Ky^-1 packed lower, per-tile partial sums
     {

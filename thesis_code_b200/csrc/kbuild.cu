@@ -39,22 +39,19 @@ __device__ __forceinline__ void build_tile(double* __restrict__ out, const doubl
                                            const double* __restrict__ Xb, const double* __restrict__ bsq,
                                            int64_t Nb, int tj, int d, int kernel_id, double variance,
                                            double diag_add, double* sm, double (*vals)[16][2]) {
-    const int dp = d | 1;
+    // the input dimension is processed in chunks of at most kMaxD columns (any d is supported)
+    const int dcap = d < kMaxD ? d : kMaxD;
+    const int dp = dcap | 1;
+    const int nchunks = (d + kMaxD - 1) / kMaxD;
     double* sa = sm;                      // [128][dp]
     double* sb = sa + GPX_TILE * dp;      // [128][dp]
     double* sasq = sb + GPX_TILE * dp;    // [128]
     double* sbsq = sasq + GPX_TILE;       // [128]
     const int tid = threadIdx.x;
-    for (int e = tid; e < GPX_TILE * d; e += blockDim.x) {
-        int rr = e / d, k = e - rr * d;
-        sa[rr * dp + k] = Xa[((int64_t)ti * GPX_TILE + rr) * d + k];
-        sb[rr * dp + k] = Xb[((int64_t)tj * GPX_TILE + rr) * d + k];
-    }
     if (tid < GPX_TILE) {
         sasq[tid] = asq[(int64_t)ti * GPX_TILE + tid];
         sbsq[tid] = bsq[(int64_t)tj * GPX_TILE + tid];
     }
-    __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int rb = 0; rb < 2; rb++) {
@@ -63,13 +60,25 @@ __device__ __forceinline__ void build_tile(double* __restrict__ out, const doubl
         double dot[16][2];
 #pragma unroll
         for (int kc = 0; kc < 16; kc++) { dot[kc][0] = 0.0; dot[kc][1] = 0.0; }
-        for (int k = 0; k < d; k++) {
-            double a = sa[r * dp + k];
+        for (int ci = 0; ci < nchunks; ci++) {
+            const int d0 = ci * kMaxD, dc = (d - d0 < kMaxD) ? (d - d0) : kMaxD;
+            if (rb == 0 || nchunks > 1) {   // a single chunk stays resident for the second row block
+                __syncthreads();
+                for (int e = tid; e < GPX_TILE * dc; e += blockDim.x) {
+                    int rr = e / dc, k = e - rr * dc;
+                    sa[rr * dp + k] = Xa[((int64_t)ti * GPX_TILE + rr) * d + d0 + k];
+                    sb[rr * dp + k] = Xb[((int64_t)tj * GPX_TILE + rr) * d + d0 + k];
+                }
+                __syncthreads();
+            }
+            for (int k = 0; k < dc; k++) {
+                double a = sa[r * dp + k];
 #pragma unroll
-            for (int kc = 0; kc < 16; kc++) {
-                int c = kc * 8 + 2 * t;
-                dot[kc][0] = fma(a, sb[c * dp + k], dot[kc][0]);
-                dot[kc][1] = fma(a, sb[(c + 1) * dp + k], dot[kc][1]);
+                for (int kc = 0; kc < 16; kc++) {
+                    int c = kc * 8 + 2 * t;
+                    dot[kc][0] = fma(a, sb[c * dp + k], dot[kc][0]);
+                    dot[kc][1] = fma(a, sb[(c + 1) * dp + k], dot[kc][1]);
+                }
             }
         }
         const double ra = sasq[r];
@@ -207,9 +216,13 @@ __global__ void detile_kernel(TileMat M, int lower, int64_t rows, int64_t cols, 
 
 }  // namespace
 
-static size_t kb_smem(int d) { return (size_t)(2 * GPX_TILE * (d | 1) + 2 * GPX_TILE) * sizeof(double); }
+static size_t kb_smem(int d) {
+    int dc = d < kMaxD ? d : kMaxD;
+    return (size_t)(2 * GPX_TILE * (dc | 1) + 2 * GPX_TILE) * sizeof(double);
+}
 
-int gpx_kbuild_max_d() { return kMaxD; }
+int gpx_kbuild_max_d() { return 1 << 20; }   // any input dimension (processed in chunks of kMaxD)
+int gpx_grad_max_d() { return kMaxD; }       // the gradient kernel keeps one partial sum per lengthscale in registers
 
 void gpx_kbuild_init() {
     size_t s = kb_smem(kMaxD);
