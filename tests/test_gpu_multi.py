@@ -20,13 +20,14 @@ rank = int(os.environ["RANK"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 nrm = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
-for cfg, N, Ns, W in [("C5", 5000, 1000, 4), ("C3", 2500, 333, 3), ("C4", 4000, 5000, 2), ("C2", 1100, 130, 1)]:
+for cfg, N, Ns, W, M in [("C5", 5000, 1000, 4, 1), ("C3", 2500, 333, 3, 4), ("C4", 4000, 5000, 2, 2), ("C2", 1100, 130, 1, 3)]:
     c = synthetic.make_config(cfg, N=N, Ns=Ns)
     kw = c["model"]["kwargs"]
     m = GPModel.from_config(kw); m.device = lr
     h = m._get_handle()                      # picks the torch.distributed group up and shards the factor
     assert h.world == dist.get_world_size()
     h.set_option("outer_tiles", W)
+    h.set_option("group_panels", M)          # delayed far updates over M panels
     m.init(c["X"], c["Y"])
     mean, var = m.get_statistics(c["Xs"], full_cov=False)
     om = o.OracleGPModel(kernel=kw["kernel"], noise_prior=kw["noise_prior"]); om.init(c["X"], c["Y"])

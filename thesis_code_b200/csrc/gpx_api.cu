@@ -148,7 +148,9 @@ struct gpx_handle {
 
     DevBuf Xs, xsq, ls, L, linv, coloff, vcoloff, linv_coloff, resid, work1, work2, alpha, scal, info;
     DevBuf stage;
-    DevBuf pbuf[2];                     // panel receive buffers (world > 1)
+    DevBuf gbuf[2];                     // group buffers (world > 1): the M panels of a group, contiguous; double buffered
+    int group_panels = 1;               // M: panels per delayed far update when sharded (measured: no gain from M = 4,
+                                        // 2587 vs 2591 ms at 4 GPUs / N = 100k, so the simpler M = 1 is the default)
     std::vector<int64_t> h_coloff;      // local offsets (-1: not owned)
     std::vector<int64_t> h_vcoloff;     // virtual full packed offsets
     std::vector<cudaEvent_t> pev;       // per-panel events (3 per panel), no timing
@@ -301,7 +303,7 @@ inline int recv_index(const gpx_t* h, int p) {
     int owned_before = (p > h->rank) ? (p - h->rank + h->world - 1) / h->world : 0;
     return p - owned_before;
 }
-inline double* recv_buf(gpx_t* h, int p) { return reinterpret_cast<double*>(h->pbuf[recv_index(h, p) & 1].p); }
+inline double* recv_buf(gpx_t* h, int p) { return reinterpret_cast<double*>(h->gbuf[recv_index(h, p) & 1].p); }  // predict sweep
 // the previous non-owned panel that used the same receive buffer as panel p (-1: none)
 inline int prev_same_buffer_panel(const gpx_t* h, int p) {
     int seen = 0;
@@ -319,10 +321,12 @@ TileMat panel_mat(gpx_t* h, int p) {
     return TileMat{recv_buf(h, p) - h->h_vcoloff[panel_begin(h, p)], ptr<int64_t>(h->vcoloff), 1};
 }
 
-cudaEvent_t pevent(gpx_t* h, int p, int which) { return h->pev[(size_t)3 * p + which]; }  // 0 ready, 1 a-done, 2 upd-done
+// per-panel events: 0 panel ready (factored / received), 3 factored on stream F; per group (stored at its first panel):
+// 1 far update of the next group's panels done, 2 far update done (group buffer free).  The predict sweep re-uses 0 / 2.
+cudaEvent_t pevent(gpx_t* h, int p, int which) { return h->pev[(size_t)4 * p + which]; }
 
 int ensure_panel_events(gpx_t* h, int npanels) {
-    size_t need = (size_t)3 * npanels;
+    size_t need = (size_t)4 * npanels;
     while (h->pev.size() < need) {
         cudaEvent_t e;
         GPX_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -385,9 +389,23 @@ void factor_panel(gpx_t* h, int p) {
     }
 }
 
-// blocked right-looking Cholesky with look-ahead + fused forward substitution.  b (work1) is consumed, z -> work2.
+// Blocked right-looking Cholesky with look-ahead, grouped ("delayed") far updates and fused forward substitution.
+// b (work1) is consumed, z -> work2.
+//
+// Panels (W tile columns, the ownership unit) are taken in groups of M.  For panel p of group g:
+//   stream F (owner of p): wait for the far update of group g-1 on p's columns, apply the NEAR updates from the
+//       earlier panels of the same group (K = W each), factor the panel;
+//   stream C: broadcast the factored panel into this group's slot of the group buffer (world > 1);
+//   stream U: forward-substitution steps with the panel; when the group is complete, the FAR update of all owned
+//       columns of later groups with K = M*W (one DMMA GEMM with four times the depth of a per-panel update: fewer
+//       passes over C, higher tile-GEMM efficiency) -- the owned panels of the NEXT group first, which is what stream
+//       F of their owners waits for, then the bulk.
+// M = 1 on one GPU (there W itself is made large); M = option "group_panels" when sharded: W stays 4 (fine-grained
+// ownership, short critical path) while the bulk update can run with K = 4 M tiles.  Measured on 2 and 4 B200s the
+// deeper update did not pay (the per-panel update is already >= 33 TFLOP/s), so the default is M = 1.
 int cholesky(gpx_t* h) {
     const int nt = h->nt, np = h->npanels, G = h->world, W = h->W;
+    const int M = (G > 1) ? (h->group_panels < 1 ? 1 : h->group_panels) : 1;
     const int max_ctas = 2 * h->num_sms;
     int rc = ensure_panel_events(h, np);
     if (rc) return rc;
@@ -396,6 +414,24 @@ int cholesky(gpx_t* h) {
         cudaEventRecord(h->tev[0], h->st);
         for (int p = 0; p < np; p++) for (int w = 0; w < 6; w++) cudaEventRecord(h->tev[1 + (size_t)6 * p + w], h->st);
     }
+    auto group_first = [&](int g) { return g * M; };
+    auto group_last = [&](int g) { int e = (g + 1) * M; return (e < np ? e : np) - 1; };
+    auto group_mat = [&](int g) -> TileMat {
+        if (G == 1) return lmat(h);
+        return TileMat{ptr<double>(h->gbuf[g & 1]) - h->h_vcoloff[panel_begin(h, group_first(g))], ptr<int64_t>(h->vcoloff), 1};
+    };
+    auto group_slot = [&](int p) -> double* {
+        const int g = p / M;
+        return ptr<double>(h->gbuf[g & 1]) + (h->h_vcoloff[panel_begin(h, p)] - h->h_vcoloff[panel_begin(h, group_first(g))]);
+    };
+    // update the columns of owned panel q (rows >= its diagonal) with the tile columns [k0, k1) of operand P
+    auto update_panel_cols = [&](TileMat P, int q, int k0, int k1, cudaStream_t st) {
+        GemmJob a{};
+        a.A = P; a.B = P; a.C = lmat(h);
+        a.tri = 1; a.i0 = panel_begin(h, q); a.i1 = nt; a.ncols = panel_end(h, q) - panel_begin(h, q); a.jbase = panel_begin(h, q);
+        a.jW = GPX_JW_CONTIG; a.jstride = 0; a.k0 = k0; a.k1 = k1; a.bdiag = 0; a.overwrite = 0;
+        gemm(h, a, st);
+    };
     cudaEvent_t ev_start;  // everything enqueued on the main stream so far (K-build, residual) is done
     GPX_CUDA(h, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
     GPX_CUDA(h, cudaEventRecord(ev_start, h->st));
@@ -403,38 +439,48 @@ int cholesky(gpx_t* h) {
     GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, ev_start, 0));
     for (int p = 0; p < np; p++) {
         const int p0 = panel_begin(h, p), p1 = panel_end(h, p);
+        const int g = p / M, gf = group_first(g), gl = group_last(g);
         const bool own = owns_panel(h, p);
+        TileMat P = group_mat(g);
         if (own) {
-            if (p > 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, pevent(h, p - 1, 1), 0));
+            // ---- stream F: everything about my own panel inside the current group ----
+            if (g > 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, pevent(h, group_first(g - 1), 1), 0));  // far-(a) of group g-1
+            for (int pp = gf; pp < p; pp++) {  // near updates from the earlier panels of this group
+                GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, pevent(h, pp, 0), 0));
+                update_panel_cols(P, p, panel_begin(h, pp), panel_end(h, pp), h->st_f);
+            }
             trace_rec(h, p, 0, h->st_f);
             factor_panel(h, p);
             trace_rec(h, p, 1, h->st_f);
-            GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_f));
-            if (G > 1) {
-                GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, p, 0), 0));
-                if ((rc = broadcast_panel(h, p, true))) return rc;
-            }
-        } else {
-            const int q = prev_same_buffer_panel(h, p);
-            if (q >= 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, q, 2), 0));  // receive buffer is free
-            if ((rc = broadcast_panel(h, p, true))) return rc;
+            GPX_CUDA(h, cudaEventRecord(pevent(h, p, 3), h->st_f));
+        }
+        if (G > 1) {
+            // ---- stream C: panel p -> this group's slot of the group buffer on every rank ----
+            if (own) GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, p, 3), 0));
+            if (p == gf && g >= 2) GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, group_first(g - 2), 2), 0));  // buffer free
+            const int root = panel_owner(h, p);
+            double* slot = group_slot(p);
+            const double* src = own ? ptr<double>(h->L) + h->h_coloff[p0] : slot;
+            double* li = ptr<double>(h->linv) + (int64_t)p0 * GPX_TILE_ELEMS;
+            GPX_NCCL(h, nccl().GroupStart());
+            ncclResult_t r1 = nccl().Broadcast(src, slot, (size_t)panel_elems(h, p), ncclDouble, root, h->comm_lo, h->st_c);
+            ncclResult_t r2 = nccl().Broadcast(li, li, (size_t)(p1 - p0) * GPX_TILE_ELEMS, ncclDouble, root, h->comm_lo, h->st_c);
+            GPX_NCCL(h, nccl().GroupEnd());
+            GPX_NCCL(h, r1);
+            GPX_NCCL(h, r2);
             GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_c));
+        } else {
+            GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_f));
         }
         // ---- stream U: consume panel p ----
         GPX_CUDA(h, cudaStreamWaitEvent(h->st, pevent(h, p, 0), 0));
         trace_rec(h, p, 2, h->st);
-        TileMat P = panel_mat(h, p);
-        const int q1 = next_owned_panel(h, p + 1);
-        // (a) the next panel's columns first when this rank owns them: that is what stream F waits for
-        int qb = q1;
-        if (q1 == p + 1 && q1 < np) {
-            GemmJob a{};
-            a.A = P; a.B = P; a.C = lmat(h);
-            a.tri = 1; a.i0 = p1; a.i1 = nt; a.ncols = panel_end(h, q1) - panel_begin(h, q1); a.jbase = panel_begin(h, q1);
-            a.jW = GPX_JW_CONTIG; a.jstride = 0; a.k0 = p0; a.k1 = p1; a.bdiag = 0; a.overwrite = 0;
-            gemm(h, a, h->st);
-            GPX_CUDA(h, cudaEventRecord(pevent(h, p, 1), h->st));
-            qb = q1 + G;
+        const int k0 = panel_begin(h, gf), k1 = panel_end(h, gl);   // the whole group as contraction range
+        if (p == gl) {
+            // far-(a): my panels of the NEXT group first -- their owners' stream F waits for this
+            for (int q = next_owned_panel(h, (g + 1) * M); q < np && q <= group_last(g + 1); q += G)
+                update_panel_cols(P, q, k0, k1, h->st);
+            GPX_CUDA(h, cudaEventRecord(pevent(h, gf, 1), h->st));
         }
         trace_rec(h, p, 3, h->st);
         // fused forward substitution with the columns of this panel (replicated right-hand side)
@@ -444,19 +490,24 @@ int cholesky(gpx_t* h) {
             h->launches++;
         }
         trace_rec(h, p, 4, h->st);
-        // (b) the rest of the owned columns
-        if (qb < np) {
-            GemmJob b{};
-            b.A = P; b.B = P; b.C = lmat(h);
-            b.tri = 1; b.i0 = p1; b.i1 = nt; b.ncols = owned_cols_from(h, qb); b.jbase = panel_begin(h, qb);
-            b.jW = W; b.jstride = W * G; b.k0 = p0; b.k1 = p1; b.bdiag = 0; b.overwrite = 0;
-            gemm(h, b, h->st);
+        if (p == gl) {
+            // far-(b): the rest of the owned columns (groups >= g+2), K = the whole group
+            const int qb = next_owned_panel(h, (g + 2) * M);
+            if (qb < np) {
+                GemmJob b{};
+                b.A = P; b.B = P; b.C = lmat(h);
+                b.tri = 1; b.i0 = panel_begin(h, qb); b.i1 = nt; b.ncols = owned_cols_from(h, qb); b.jbase = panel_begin(h, qb);
+                b.jW = W; b.jstride = W * G; b.k0 = k0; b.k1 = k1; b.bdiag = 0; b.overwrite = 0;
+                gemm(h, b, h->st);
+            }
+            GPX_CUDA(h, cudaEventRecord(pevent(h, gf, 2), h->st));
         }
-        GPX_CUDA(h, cudaEventRecord(pevent(h, p, 2), h->st));
         trace_rec(h, p, 5, h->st);
         if (!h->lookahead) {  // debugging aid: serialise the three streams
-            GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, pevent(h, p, 2), 0));
-            GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, p, 2), 0));
+            cudaEvent_t e = pevent(h, p, 3);   // re-used as a scratch event: panel p's own "factored" role is over
+            GPX_CUDA(h, cudaEventRecord(e, h->st));
+            GPX_CUDA(h, cudaStreamWaitEvent(h->st_f, e, 0));
+            GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, e, 0));
         }
     }
     // join F and C into the main stream
@@ -549,7 +600,7 @@ void gpx_destroy(gpx_t* h) {
     if (h->comm_lo && h->comm_lo != h->comm) nccl().CommDestroy(h->comm_lo);
     if (h->comm) nccl().CommDestroy(h->comm);
     DevBuf* all[] = {&h->Xs, &h->xsq, &h->ls, &h->L, &h->linv, &h->coloff, &h->vcoloff, &h->linv_coloff, &h->resid,
-                     &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->pbuf[0], &h->pbuf[1], &h->Tt,
+                     &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->gbuf[0], &h->gbuf[1], &h->Tt,
                      &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar};
     for (DevBuf* b : all) release(h, *b);
     for (auto& e : h->ev) cudaEventDestroy(e);
@@ -608,6 +659,7 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "sync_phases")) { h->sync_phases = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_timing")) { h->gemm_timing = value ? 1 : 0; return 0; }
     if (!strcmp(name, "lookahead")) { h->lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "group_panels")) { if (value < 1 || value > 16) return fail(h, -1, "group_panels out of range"); h->group_panels = (int)value; h->fitted = false; return 0; }
     if (!strcmp(name, "nccl_lo_ctas")) { h->nccl_lo_ctas = (int)value; return 0; }  // takes effect at gpx_comm_init
     if (!strcmp(name, "trace")) { h->trace = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_max_chunk")) { h->gemm_max_chunk = (int)value; return 0; }
@@ -691,8 +743,12 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     if ((rc = ensure(h, h->scal, 64))) return rc;
     if ((rc = ensure(h, h->info, 64))) return rc;
     if (G > 1) {
-        if ((rc = ensure(h, h->pbuf[0], (size_t)max_panel * 8))) return rc;
-        if ((rc = ensure(h, h->pbuf[1], (size_t)max_panel * 8))) return rc;
+        const int Mg = h->group_panels < 1 ? 1 : h->group_panels;
+        int64_t group_elems = 0;   // the first group is the largest
+        for (int p = 0; p < Mg && p < h->npanels; p++) group_elems += panel_elems(h, p);
+        if (group_elems < max_panel) group_elems = max_panel;
+        if ((rc = ensure(h, h->gbuf[0], (size_t)group_elems * 8))) return rc;
+        if ((rc = ensure(h, h->gbuf[1], (size_t)group_elems * 8))) return rc;
     }
     GPX_CUDA(h, cudaMemcpyAsync(h->coloff.p, h->h_coloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
     GPX_CUDA(h, cudaMemcpyAsync(h->vcoloff.p, h->h_vcoloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
