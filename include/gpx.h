@@ -120,9 +120,11 @@ GPX_API int gpx_set_option(gpx_t* h, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel of this handle is launched on, so that a caller can
  * bracket calls with its own CUDA events (bench.py does, via torch.cuda.ExternalStream). */
 GPX_API void* gpx_stream(const gpx_t* h);
-/* With option "gemm_timing"=1 every launch of the DMMA tile-GEMM kernel is bracketed by CUDA events; this returns
- * (and resets) the accumulated device time in ms, the fp64 flops those launches issued (2*128^3 per tile-k step)
- * and their count.  Used for the roofline of the dominant kernel. */
+/* With option "gemm_timing"=1 every launch of the DMMA tile-GEMM kernel on the handle's main stream (the trailing /
+ * far updates of the Cholesky and the whole variance solve; the small panel-factorisation GEMMs run concurrently on a
+ * second stream and are left out so that no wall time is counted twice) is bracketed by CUDA events; this returns
+ * (and resets) the accumulated device time in ms, the fp64 flops those launches performed (2*128^3 per output tile
+ * and k-tile) and their count.  Used for the roofline of the dominant kernel. */
 GPX_API int gpx_gemm_stats(gpx_t* h, double* total_ms, double* issued_flops, int64_t* launches);
 /* With option "trace"=1 the Cholesky records a per-panel timeline: 6 doubles per outer panel (ms since the start of
  * the factorisation on this rank): factor start, factor end (owner only), panel ready on the update stream, next-panel

@@ -243,10 +243,11 @@ int to_device(gpx_t* h, const double* src, size_t count, int mem, DevBuf& stagin
 void gemm(gpx_t* h, const GemmJob& job_in, cudaStream_t st) {
     GemmJob job = job_in;
     job.chunk = h->gemm_max_chunk > 0 ? h->gemm_max_chunk : (h->world > 1 ? 4 : 16);
-    if (!h->gemm_timing) {
+    // Only launches on the main (update) stream are timed and counted: the panel-factorisation GEMMs of stream F
+    // overlap them, so adding their durations would count the same wall time twice.
+    if (!h->gemm_timing || st != h->st) {
         long long steps = gpx_launch_gemm(job, h->num_sms, st, &h->launches);
-        h->gemm_flops += 2.0 * 128 * 128 * 128 * (double)steps;
-        if (steps) h->gemm_launches++;
+        if (steps && st == h->st) { h->gemm_flops += 2.0 * 128 * 128 * 128 * (double)steps; h->gemm_launches++; }
         return;
     }
     if (h->gemm_ev_used + 2 > h->gemm_ev.size()) {
@@ -264,8 +265,7 @@ void gemm(gpx_t* h, const GemmJob& job_in, cudaStream_t st) {
     }
 }
 
-// fold the recorded per-launch event pairs into gemm_ms (all streams must be idle).  With look-ahead the panel
-// kernels of stream F overlap the updates of stream U, so the sum can exceed the wall time of the phase.
+// fold the recorded per-launch event pairs into gemm_ms (the main stream must be idle)
 void gemm_collect(gpx_t* h) {
     for (size_t i = 0; i + 1 < h->gemm_ev_used; i += 2) {
         float ms = 0.f;
