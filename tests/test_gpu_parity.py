@@ -357,3 +357,37 @@ def test_hmc_hyper_posterior_gives_leading_sample_axis():
         st = o.fit(X, Y, "GPyRBF", th[0], th[1:2], False, th[2])
         om, ov = o.predict(st, Xs)
         assert normwise(mean[i], om) < TOL and normwise(var[i], ov) < TOL
+
+
+def test_randomised_small_cases_vs_oracle(gpu_handle):
+    """Seeded random sweep over sizes (incl. ragged N around the 128 tile edge), dimensions, kernels, ARD, noise levels,
+    output counts and constant means: fit + predict + LML through the C ABI vs the oracle."""
+    rng = np.random.RandomState(2024)
+    names = list(_gpx.KERNEL_IDS)
+    sizes = [1, 2, 5, 127, 128, 129, 255, 256, 257, 300, 383, 385, 511, 640]
+    for case in range(40):
+        N = int(sizes[case % len(sizes)] if case < 28 else rng.randint(1, 700))
+        d = int(rng.randint(1, 13))
+        O = int(rng.choice([1, 1, 1, 2, 3]))
+        Ns = int(rng.choice([1, 7, 128, 129, 300]))
+        name = names[rng.randint(4)]
+        ARD = bool(rng.randint(2))
+        ls = rng.uniform(0.3, 2.0, d if ARD else 1)
+        variance = float(rng.uniform(0.2, 3.0))
+        noise = float(10 ** rng.uniform(-4, 0))
+        mean_const = float(rng.choice([0.0, rng.randn()]))
+        X = rng.randn(N, d)
+        Y = rng.randn(N, O) + mean_const
+        Xs = rng.randn(Ns, d)
+        gpu_handle.set_option("outer_tiles", int(rng.choice([0, 1, 2, 5])))
+        gpu_handle.fit(X, Y, _gpx.KERNEL_IDS[name], variance, ls, noise, mean_const=mean_const)
+        mean, var = gpu_handle.predict(Xs, output_dim=O)
+        st = o.fit(X, Y, name, variance, ls, ARD, noise, mean_const=mean_const)
+        om, ov = o.predict(st, Xs)
+        tag = (case, N, d, O, Ns, name, ARD)
+        assert normwise(mean, om) < TOL, tag
+        assert normwise(var, ov[:, 0]) < TOL, tag
+        assert abs(gpu_handle.lml()[0] - st["lml"]) <= TOL * max(1.0, abs(st["lml"])), tag
+        alpha, _ = gpu_handle.export(N, O)
+        assert normwise(alpha, st["alpha"]) < 1e-6, tag
+    gpu_handle.set_option("outer_tiles", 0)
