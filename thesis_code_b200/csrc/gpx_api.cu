@@ -1229,6 +1229,35 @@ GPX_API double gpx_debug_gemm(gpx_t* h, int rows, int cols, int ktiles, int over
     return cudaGetLastError() == cudaSuccess ? ms / reps : -3.0;
 }
 
+// Development aid: mean device time (us) of the diagonal-tile POTRF+inverse kernel on a well-conditioned SPD tile.
+GPX_API double gpx_debug_potrf(gpx_t* h, int reps) {
+    if (!h) return -1.0;
+    cudaSetDevice(h->device);
+    DevBuf src, work, inv, info;
+    if (ensure(h, src, GPX_TILE_BYTES) || ensure(h, work, GPX_TILE_BYTES) || ensure(h, inv, GPX_TILE_BYTES) || ensure(h, info, 64)) return -2.0;
+    std::vector<double> t(GPX_TILE_ELEMS);
+    for (int r = 0; r < GPX_TILE; r++)
+        for (int c = 0; c < GPX_TILE; c++) t[gpx_tile_idx(r, c)] = (r == c ? 4.0 : 0.0) + exp(-0.01 * (r - c) * (r - c));
+    cudaMemcpy(src.p, t.data(), GPX_TILE_BYTES, cudaMemcpyHostToDevice);
+    cudaMemset(info.p, 0, 64);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float total = 0.f;
+    for (int r = 0; r < reps + 1; r++) {
+        cudaMemcpyAsync(work.p, src.p, GPX_TILE_BYTES, cudaMemcpyDeviceToDevice, h->st);
+        cudaEventRecord(e0, h->st);
+        gpx_launch_potrf_tile(ptr<double>(work), ptr<double>(inv), ptr<int>(info), 0, h->st);
+        cudaEventRecord(e1, h->st);
+        cudaStreamSynchronize(h->st);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0) total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (DevBuf* b : {&src, &work, &inv, &info}) release(h, *b);
+    return 1e3 * total / reps;
+}
+
 int gpx_export(gpx_t* h, double* alpha, double* Lout) {
     if (!h) return -1;
     if (!h->fitted) return fail(h, -1, "gpx_export called before a successful gpx_fit");

@@ -18,12 +18,16 @@ namespace {
 constexpr int kNB = 32;                 // 4x4 blocks per dimension
 constexpr int kOwners = kNB * (kNB + 1) / 2;   // 528
 constexpr int kThreadsP = 544;
-constexpr int kLP = 132;                // pitch of the shared copy of L (doubles)
+constexpr int kBS = 18;                 // doubles per published 4x4 block: 16 + 2 padding.  With a 128 B pitch every lane of
+                                        // a warp (consecutive bj) hit the same banks: 32-way conflicts made this kernel
+                                        // 129 us; 144 B spreads a warp's double2 loads over all banks (tools/gemm_bench.py)
 
 struct PotrfSmem {
-    double Lf[GPX_TILE * kLP];          // final L, row-major with pitch (for the inverse phase)
-    double P[2][GPX_TILE * 4];          // published 4-column panel, block-contiguous: [bi*16 + r*4 + c]
-    double Xr[2][GPX_TILE * 4];         // published 4-row block row of the inverse: [bj*16 + r*4 + c]
+    double Lf[kNB * kNB * kBS];         // final L for the inverse phase, 4x4 blocks, block (bi, k) at (k*32 + bi)*kBS: the
+                                        // writers (one block column, consecutive bi) and the readers (one block per warp,
+                                        // broadcast) are both conflict-free
+    double P[2][kNB * kBS];             // published 4-column panel, block-contiguous: [bi*kBS + r*4 + c]
+    double Xr[2][kNB * kBS];            // published 4-row block row of the inverse: [bj*kBS + r*4 + c]
     double Dinv[kNB][16];               // inverted 4x4 diagonal blocks
 };
 
@@ -60,7 +64,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) potrf_tile_kernel(double* __rest
     for (int kb = 0; kb < kNB; kb++) {
         const int buf = kb & 1;
         if (owner && bj == kb && bi == kb) {
-            // factor the 4x4 diagonal block in registers
+            // factor the 4x4 diagonal block in registers.  rsqrt (MUFU + Newton, ~1 ulp) replaces sqrt + two divisions
+            // per column on this single-thread critical path: L_jj = d * rsqrt(d), 1 / L_jj = rsqrt(d).
+            double rinv[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 double d = b[j][j];
@@ -68,9 +74,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) potrf_tile_kernel(double* __rest
                     atomicCAS(info, 0, col_index * GPX_TILE + 4 * kb + j + 1);
                     d = 1.0;
                 }
-                const double s = sqrt(d);
-                const double inv = 1.0 / s;
-                b[j][j] = s;
+                const double inv = rsqrt(d);
+                rinv[j] = inv;
+                b[j][j] = d * inv;
 #pragma unroll
                 for (int i = j + 1; i < 4; i++) b[i][j] *= inv;
 #pragma unroll
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) potrf_tile_kernel(double* __rest
             for (int r = 0; r < 4; r++)
 #pragma unroll
                 for (int c = r + 1; c < 4; c++) b[r][c] = 0.0;
-            // invert the lower 4x4
+            // invert the lower 4x4 (multiplications by the stored reciprocals only)
             double di[4][4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -91,13 +97,13 @@ __global__ void __launch_bounds__(kThreadsP, 1) potrf_tile_kernel(double* __rest
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                di[j][j] = 1.0 / b[j][j];
+                di[j][j] = rinv[j];
 #pragma unroll
                 for (int i = j + 1; i < 4; i++) {
                     double s = 0.0;
 #pragma unroll
                     for (int k = j; k < i; k++) s += b[i][k] * di[k][j];
-                    di[i][j] = -s / b[i][i];
+                    di[i][j] = -s * rinv[i];
                 }
             }
 #pragma unroll
@@ -128,13 +134,13 @@ __global__ void __launch_bounds__(kThreadsP, 1) potrf_tile_kernel(double* __rest
 #pragma unroll
                 for (int r = 0; r < 4; r++)
 #pragma unroll
-                    for (int c = 0; c < 4; c++) S.P[buf][bi * 16 + r * 4 + c] = b[r][c];
+                    for (int c = 0; c < 4; c++) S.P[buf][bi * kBS + r * 4 + c] = b[r][c];
             }
             // this block of L is final: keep a shared copy for the inverse phase and write it to global memory
 #pragma unroll
             for (int r = 0; r < 4; r++) {
 #pragma unroll
-                for (int c = 0; c < 4; c++) S.Lf[(4 * bi + r) * kLP + 4 * bj + c] = b[r][c];
+                for (int c = 0; c < 4; c++) S.Lf[(bj * kNB + bi) * kBS + r * 4 + c] = b[r][c];
                 double2* p = reinterpret_cast<double2*>(blk_ptr(tile, bi, bj, r));
                 p[0] = make_double2(b[r][0], b[r][1]);
                 p[1] = make_double2(b[r][2], b[r][3]);
@@ -144,8 +150,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) potrf_tile_kernel(double* __rest
         if (owner && bj > kb) {
             // rank-4 update: b[r][c] -= sum_k P[bi][r][k] * P[bj][c][k]
             double pa[4][4], pb[4][4];
-            const double2* qa = reinterpret_cast<const double2*>(&S.P[buf][bi * 16]);
-            const double2* qb = reinterpret_cast<const double2*>(&S.P[buf][bj * 16]);
+            const double2* qa = reinterpret_cast<const double2*>(&S.P[buf][bi * kBS]);
+            const double2* qb = reinterpret_cast<const double2*>(&S.P[buf][bj * kBS]);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 double2 a0 = qa[2 * r], a1 = qa[2 * r + 1], c0 = qb[2 * r], c1 = qb[2 * r + 1];
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) potrf_tile_kernel(double* __rest
 #pragma unroll
             for (int r = 0; r < 4; r++) {
 #pragma unroll
-                for (int c = 0; c < 4; c++) S.Xr[buf][bj * 16 + r * 4 + c] = x[r][c];
+                for (int c = 0; c < 4; c++) S.Xr[buf][bj * kBS + r * 4 + c] = x[r][c];
                 double2* p = reinterpret_cast<double2*>(blk_ptr(inv_tile, bi, bj, r));
                 p[0] = make_double2(x[r][0], x[r][1]);
                 p[1] = make_double2(x[r][2], x[r][3]);
@@ -203,10 +209,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) potrf_tile_kernel(double* __rest
         if (owner && bi > k && bj <= k) {
             // U(bi,bj) -= L(bi,k) * X(k,bj)
             double l[4][4], x[4][4];
-            const double2* qx = reinterpret_cast<const double2*>(&S.Xr[buf][bj * 16]);
+            const double2* qx = reinterpret_cast<const double2*>(&S.Xr[buf][bj * kBS]);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const double2* ql = reinterpret_cast<const double2*>(&S.Lf[(4 * bi + r) * kLP + 4 * k]);
+                const double2* ql = reinterpret_cast<const double2*>(&S.Lf[(k * kNB + bi) * kBS + r * 4]);
                 double2 l0 = ql[0], l1 = ql[1], x0 = qx[2 * r], x1 = qx[2 * r + 1];
                 l[r][0] = l0.x; l[r][1] = l0.y; l[r][2] = l1.x; l[r][3] = l1.y;
                 x[r][0] = x0.x; x[r][1] = x0.y; x[r][2] = x1.x; x[r][3] = x1.y;

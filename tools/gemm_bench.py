@@ -6,6 +6,8 @@ h = _gpx.Handle(0)
 f = h.lib.gpx_debug_gemm
 f.restype = ctypes.c_double
 f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+g = h.lib.gpx_debug_potrf; g.restype = ctypes.c_double; g.argtypes = [ctypes.c_void_p, ctypes.c_int]
+print("potrf_tile_kernel (128x128 Cholesky + inverse): %.1f us per launch" % g(h._h, 50))
 print("rows cols K overwrite chunk :   ms    TFLOP/s")
 for (rows, cols, K, ow, ch) in [(148, 64, 1, 0, 16), (148, 64, 2, 0, 16), (148, 64, 4, 0, 16), (148, 64, 8, 0, 16), (148, 64, 16, 0, 16),
                                 (148, 64, 4, 1, 16), (148, 64, 1, 1, 16), (148, 64, 4, 0, 1), (148, 64, 4, 0, 4), (148, 64, 4, 0, 64),
