@@ -137,3 +137,25 @@ def test_normalizer_model_wraps_any_model(tmp_path):
     nm = pkg.NormalizerModel.from_config({"model": {"name": "GPModel", "kwargs": {"kernel": {"name": "GPyRBF"}, "noise_prior": 0.1}},
                                           "normalize_output": False})
     assert isinstance(nm.model, pkg.GPModel) and nm._normalize_input and not nm._normalize_output
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (produced by bench.py on B200s) carry every key the driver's contract names."""
+    import glob
+    import json
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_c*gpu.json")))
+    assert len(files) >= 3
+    for f in files:
+        line = json.loads(open(f).read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+            assert key in line, (f, key)
+        assert line["dtype"] == "f64" and line["data"] == "synthetic" and line["vs_baseline"] is None
+        assert "workload" in line["config"] and "model" not in line["config"]
+        r = line["roofline"]
+        assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert 0.5 < r["frac"] < 1.05                                  # a DMMA-bound kernel close to, not above, the measured peak
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"]) and line["cpu_baseline"]["kind"] == "port"
+        assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
