@@ -115,7 +115,9 @@ GPX_API int64_t gpx_launch_count(const gpx_t* h);
  * "predict_batch_tiles" (test tiles per variance batch), "sync_phases" (1: bracket phases with events),
  * "gemm_timing" (1: per-launch events on the tile-GEMM kernel, see gpx_gemm_stats), "lookahead" (0: serialise the
  * factor / communication / update streams), "gemm_max_chunk" (cap on tile slots per CTA), "group_panels" (panels per delayed far update when sharded, default 1),
- * "nccl_lo_ctas" (CTA cap of the factorisation communicator, default 4; before gpx_comm_init), "trace" (see gpx_trace). */
+ * "nccl_lo_ctas" (CTA cap of the factorisation communicator, default 4; before gpx_comm_init), "cache_mb" (sharded
+ * handles keep received panels resident for later predicts: -1 = as many as fit beside a reserve, 0 = none, else a cap
+ * in MB), "trace" (see gpx_trace). */
 GPX_API int gpx_set_option(gpx_t* h, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel of this handle is launched on, so that a caller can
  * bracket calls with its own CUDA events (bench.py does, via torch.cuda.ExternalStream). */

@@ -20,7 +20,9 @@ rank = int(os.environ["RANK"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 nrm = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
-for cfg, N, Ns, W, M in [("C5", 5000, 1000, 4, 1), ("C3", 2500, 333, 3, 4), ("C4", 4000, 5000, 2, 2), ("C2", 1100, 130, 1, 3)]:
+# (config, N, N*, outer_tiles, group_panels, cache_mb): resident-panel cache on / partial / off, delayed far updates
+for cfg, N, Ns, W, M, cache in [("C5", 5000, 1000, 4, 1, -1), ("C5", 5000, 1000, 4, 1, 20), ("C3", 2500, 333, 3, 4, -1),
+                                ("C4", 4000, 5000, 2, 2, -1), ("C2", 1100, 130, 1, 3, -1), ("C2", 3000, 700, 1, 1, 0)]:
     c = synthetic.make_config(cfg, N=N, Ns=Ns)
     kw = c["model"]["kwargs"]
     m = GPModel.from_config(kw); m.device = lr
@@ -28,6 +30,7 @@ for cfg, N, Ns, W, M in [("C5", 5000, 1000, 4, 1), ("C3", 2500, 333, 3, 4), ("C4
     assert h.world == dist.get_world_size()
     h.set_option("outer_tiles", W)
     h.set_option("group_panels", M)          # delayed far updates over M panels
+    h.set_option("cache_mb", cache)
     m.init(c["X"], c["Y"])
     mean, var = m.get_statistics(c["Xs"], full_cov=False)
     om = o.OracleGPModel(kernel=kw["kernel"], noise_prior=kw["noise_prior"]); om.init(c["X"], c["Y"])

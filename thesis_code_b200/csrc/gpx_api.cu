@@ -151,6 +151,11 @@ struct gpx_handle {
     DevBuf gbuf[2];                     // group buffers (world > 1): the M panels of a group, contiguous; double buffered
     int group_panels = 1;               // M: panels per delayed far update when sharded (measured: no gain from M = 4,
                                         // 2587 vs 2591 ms at 4 GPUs / N = 100k, so the simpler M = 1 is the default)
+    DevBuf cache;                       // received panels kept resident after the fit (world > 1) so that predict does not
+    DevBuf ucoloff;                     // have to re-broadcast them; ucoloff = column offsets of own + cached columns
+    std::vector<int64_t> h_ucoloff;     // relative to the base of L (pointer arithmetic across the two allocations)
+    int cache_panels = 0;               // panels [0, cache_panels) are resident on every rank
+    int64_t cache_limit_mb = -1;        // option "cache_mb": -1 auto (free memory minus a reserve), 0 disables
     std::vector<int64_t> h_coloff;      // local offsets (-1: not owned)
     std::vector<int64_t> h_vcoloff;     // virtual full packed offsets
     std::vector<cudaEvent_t> pev;       // per-panel events (3 per panel), no timing
@@ -315,9 +320,18 @@ inline int prev_same_buffer_panel(const gpx_t* h, int p) {
 
 TileMat lmat(gpx_t* h) { return TileMat{ptr<double>(h->L), ptr<int64_t>(h->coloff), 1}; }
 TileMat linvmat(gpx_t* h) { return TileMat{ptr<double>(h->linv), ptr<int64_t>(h->linv_coloff), 1}; }
-// the factored panel p as an operand: the local storage on its owner, the receive buffer elsewhere
+// own + cached columns through one table (offsets relative to L's base)
+TileMat umat(gpx_t* h) { return TileMat{ptr<double>(h->L), ptr<int64_t>(h->ucoloff), 1}; }
+inline bool panel_cached(const gpx_t* h, int p) { return h->world > 1 && p < h->cache_panels && !owns_panel(h, p); }
+// where a non-owned panel is received: its resident cache slot, or one of the two rotating buffers
+inline double* panel_recv_ptr(gpx_t* h, int p) {
+    if (panel_cached(h, p)) return ptr<double>(h->L) + h->h_ucoloff[panel_begin(h, p)];
+    return recv_buf(h, p);
+}
+// the factored panel p as an operand: the local storage on its owner, the cache or a receive buffer elsewhere
 TileMat panel_mat(gpx_t* h, int p) {
     if (owns_panel(h, p)) return lmat(h);
+    if (panel_cached(h, p)) return umat(h);
     return TileMat{recv_buf(h, p) - h->h_vcoloff[panel_begin(h, p)], ptr<int64_t>(h->vcoloff), 1};
 }
 
@@ -344,7 +358,7 @@ int broadcast_panel(gpx_t* h, int p, bool with_linv) {
     ncclComm_t comm = with_linv ? h->comm_lo : h->comm;
     const int p0 = panel_begin(h, p), p1 = panel_end(h, p), root = panel_owner(h, p);
     const int64_t elems = panel_elems(h, p);
-    double* buf = owns_panel(h, p) ? ptr<double>(h->L) + h->h_coloff[p0] : recv_buf(h, p);
+    double* buf = owns_panel(h, p) ? ptr<double>(h->L) + h->h_coloff[p0] : panel_recv_ptr(h, p);
     GPX_NCCL(h, nccl().GroupStart());
     ncclResult_t r1 = nccl().Broadcast(buf, buf, (size_t)elems, ncclDouble, root, comm, h->st_c);
     ncclResult_t r2 = ncclSuccess;
@@ -416,12 +430,23 @@ int cholesky(gpx_t* h) {
     }
     auto group_first = [&](int g) { return g * M; };
     auto group_last = [&](int g) { int e = (g + 1) * M; return (e < np ? e : np) - 1; };
+    // operand view of group g / receive slot of panel p.  With M == 1 (default) a panel is used in place on its owner,
+    // lives in its resident cache slot when cached, and otherwise in one of the two rotating buffers; with M > 1 the
+    // whole group (own panels included) is assembled contiguously in a rotating group buffer.
     auto group_mat = [&](int g) -> TileMat {
         if (G == 1) return lmat(h);
+        if (M == 1) {
+            if (owns_panel(h, g)) return lmat(h);
+            if (panel_cached(h, g)) return umat(h);
+        }
         return TileMat{ptr<double>(h->gbuf[g & 1]) - h->h_vcoloff[panel_begin(h, group_first(g))], ptr<int64_t>(h->vcoloff), 1};
     };
     auto group_slot = [&](int p) -> double* {
         const int g = p / M;
+        if (M == 1) {
+            if (owns_panel(h, p)) return ptr<double>(h->L) + h->h_coloff[panel_begin(h, p)];
+            if (panel_cached(h, p)) return ptr<double>(h->L) + h->h_ucoloff[panel_begin(h, p)];
+        }
         return ptr<double>(h->gbuf[g & 1]) + (h->h_vcoloff[panel_begin(h, p)] - h->h_vcoloff[panel_begin(h, group_first(g))]);
     };
     // update the columns of owned panel q (rows >= its diagonal) with the tile columns [k0, k1) of operand P
@@ -600,7 +625,8 @@ void gpx_destroy(gpx_t* h) {
     if (h->comm_lo && h->comm_lo != h->comm) nccl().CommDestroy(h->comm_lo);
     if (h->comm) nccl().CommDestroy(h->comm);
     DevBuf* all[] = {&h->Xs, &h->xsq, &h->ls, &h->L, &h->linv, &h->coloff, &h->vcoloff, &h->linv_coloff, &h->resid,
-                     &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->gbuf[0], &h->gbuf[1], &h->Tt,
+                     &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->gbuf[0], &h->gbuf[1], &h->cache,
+                     &h->ucoloff, &h->Tt,
                      &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar};
     for (DevBuf* b : all) release(h, *b);
     for (auto& e : h->ev) cudaEventDestroy(e);
@@ -659,6 +685,7 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "sync_phases")) { h->sync_phases = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_timing")) { h->gemm_timing = value ? 1 : 0; return 0; }
     if (!strcmp(name, "lookahead")) { h->lookahead = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "cache_mb")) { h->cache_limit_mb = value; h->fitted = false; return 0; }
     if (!strcmp(name, "group_panels")) { if (value < 1 || value > 16) return fail(h, -1, "group_panels out of range"); h->group_panels = (int)value; h->fitted = false; return 0; }
     if (!strcmp(name, "nccl_lo_ctas")) { h->nccl_lo_ctas = (int)value; return 0; }  // takes effect at gpx_comm_init
     if (!strcmp(name, "trace")) { h->trace = value ? 1 : 0; return 0; }
@@ -749,6 +776,51 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
         if (group_elems < max_panel) group_elems = max_panel;
         if ((rc = ensure(h, h->gbuf[0], (size_t)group_elems * 8))) return rc;
         if ((rc = ensure(h, h->gbuf[1], (size_t)group_elems * 8))) return rc;
+    }
+    // Panel cache (world > 1, M == 1): keep as many received panels [0, cache_panels) resident as fit beside a reserve
+    // for the predict workspaces, so that predict sweeps do not re-broadcast them.  Every rank must take the same
+    // decision: the budget is the minimum over ranks and the panel count is derived from sizes all ranks know.
+    h->cache_panels = 0;
+    h->h_ucoloff.assign(nt, -1);
+    if (G > 1) {
+        if ((rc = ensure(h, h->ucoloff, (size_t)nt * 8))) return rc;
+        const int Mg = h->group_panels < 1 ? 1 : h->group_panels;
+        double budget = 0.0;
+        if (Mg == 1 && h->cache_limit_mb != 0) {
+            size_t fr = 0, tot = 0;
+            GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
+            fr += h->cache.bytes;   // reusable
+            double reserve = 0.35 * (double)fr > 16e9 ? 0.35 * (double)fr : 16e9;   // predict workspaces, NCCL, the caller
+            budget = (double)fr > reserve ? (double)fr - reserve : 0.0;
+            if (h->cache_limit_mb > 0 && budget > 1e6 * (double)h->cache_limit_mb) budget = 1e6 * (double)h->cache_limit_mb;
+        }
+        double* ds = ptr<double>(h->scal) + 5;
+        GPX_CUDA(h, cudaMemcpyAsync(ds, &budget, 8, cudaMemcpyHostToDevice, h->st));
+        GPX_NCCL(h, nccl().AllReduce(ds, ds, 1, ncclDouble, ncclMin, h->comm, h->st));
+        GPX_CUDA(h, cudaMemcpyAsync(&budget, ds, 8, cudaMemcpyDeviceToHost, h->st));
+        GPX_CUDA(h, cudaStreamSynchronize(h->st));
+        // largest P such that every rank's non-owned panels below P fit the common budget
+        std::vector<double> need(G, 0.0);
+        int P = 0;
+        for (; P < h->npanels; P++) {
+            const double bytes = 8.0 * (double)panel_elems(h, P);
+            bool ok = true;
+            for (int r = 0; r < G; r++) if (r != panel_owner(h, P) && need[r] + bytes > budget) ok = false;
+            if (!ok) break;
+            for (int r = 0; r < G; r++) if (r != panel_owner(h, P)) need[r] += bytes;
+        }
+        h->cache_panels = P;
+        int64_t coff = 0;
+        for (int pp = 0; pp < P; pp++) if (!owns_panel(h, pp)) coff += panel_elems(h, pp);
+        if ((rc = ensure(h, h->cache, (size_t)(coff > 0 ? coff : 1) * 8))) return rc;
+        const int64_t base_delta = (int64_t)(ptr<double>(h->cache) - ptr<double>(h->L));   // in elements
+        coff = 0;
+        for (int c = 0; c < nt; c++) {
+            const int pp = c / h->W;
+            if (panel_owner(h, pp) == h->rank) h->h_ucoloff[c] = h->h_coloff[c];
+            else if (pp < P) { h->h_ucoloff[c] = base_delta + coff; coff += (int64_t)(nt - c) * GPX_TILE_ELEMS; }
+        }
+        GPX_CUDA(h, cudaMemcpyAsync(h->ucoloff.p, h->h_ucoloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
     }
     GPX_CUDA(h, cudaMemcpyAsync(h->coloff.p, h->h_coloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
     GPX_CUDA(h, cudaMemcpyAsync(h->vcoloff.p, h->h_vcoloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
@@ -902,11 +974,13 @@ static int var_trsm(gpx_t* h, TileMat Tt, int nb) {
     GPX_CUDA(h, cudaEventRecord(ev_start, h->st));
     GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, ev_start, 0));  // previous users of the panel buffers are done
     for (int p = 0; p < np; p++) {
-        const int q = owns_panel(h, p) ? -1 : prev_same_buffer_panel(h, p);
-        if (q >= 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, q, 2), 0));
-        if ((rc = broadcast_panel(h, p, false))) return rc;
-        GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_c));
-        GPX_CUDA(h, cudaStreamWaitEvent(h->st, pevent(h, p, 0), 0));
+        if (p >= h->cache_panels) {   // panels below cache_panels are resident on every rank since the fit
+            const int q = owns_panel(h, p) ? -1 : prev_same_buffer_panel(h, p);
+            if (q >= 0) GPX_CUDA(h, cudaStreamWaitEvent(h->st_c, pevent(h, q, 2), 0));
+            if ((rc = broadcast_panel(h, p, false))) return rc;
+            GPX_CUDA(h, cudaEventRecord(pevent(h, p, 0), h->st_c));
+            GPX_CUDA(h, cudaStreamWaitEvent(h->st, pevent(h, p, 0), 0));
+        }
         if (nb > 0) var_trsm_panel(h, Tt, nb, panel_mat(h, p), p);
         GPX_CUDA(h, cudaEventRecord(pevent(h, p, 2), h->st));
     }

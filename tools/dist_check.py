@@ -21,6 +21,7 @@ for cfg, N, Ns, W in cases:
     kid = _gpx.KERNEL_IDS[kw['kernel']['name']]
     h.set_option("outer_tiles", W)
     if os.environ.get("GPX_MAX_CHUNK"): h.set_option("gemm_max_chunk", int(os.environ["GPX_MAX_CHUNK"]))
+    if os.environ.get("GPX_CACHE_MB"): h.set_option("cache_mb", int(os.environ["GPX_CACHE_MB"]))
     if os.environ.get("GPX_GROUP"): h.set_option("group_panels", int(os.environ["GPX_GROUP"]))
     if os.environ.get("GPX_TRACE"): h.set_option("trace", 1)
     if os.environ.get("GPX_LOOKAHEAD"): h.set_option("lookahead", int(os.environ["GPX_LOOKAHEAD"]))
