@@ -370,6 +370,16 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         self._ensure_fitted(self._current_thetas[0])
         return self._get_handle().lml()[0]
 
+    def predict_jacobian(self, X, full_cov=True):
+        """Reference core_models.py:313-333.  There the method reads ``self.normalizer``, an attribute GPModel never
+        defines, so it cannot run as written; not built here."""
+        raise NotImplementedError("predict_jacobian is not built (the reference version depends on an undefined "
+                                  "`self.normalizer`); see SURVEY.md section 8(f)")
+
+    def predict_hessian(self, X, full_cov=True):
+        """Reference core_models.py:335-380 (RBF only, same undefined ``self.normalizer``); not built here."""
+        raise NotImplementedError("predict_hessian is not built; see SURVEY.md section 8(f)")
+
     def phase_times_ms(self):
         """Per-phase CUDA-event times of the last fit / predict (the numbers Runner logs as time.training/pred)."""
         return self._get_handle().phase_ms()
