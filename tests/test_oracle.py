@@ -180,3 +180,29 @@ def test_hmc_sampler_recipe():
     assert s1.shape == (24, 3) and np.array_equal(s1, s2) and np.all(s1 > 0)
     assert obj(s1[-1])[0] > obj(s1[0])[0] + 20
     assert len(np.unique(s1[:, 0])) > 5                                            # proposals are being accepted
+
+
+def test_oracle_vs_sklearn_random_cases():
+    """Beyond the committed fixtures: 24 seeded random problems, oracle vs scikit-learn run live (mean, variance, LML)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern
+    nu = {"GPyMatern52": 2.5, "GPyMatern32": 1.5, "GPyExponential": 0.5}
+    rng = np.random.RandomState(99)
+    for case in range(24):
+        name = o.KERNEL_NAMES[case % 4]
+        N, d = int(rng.randint(2, 120)), int(rng.randint(1, 6))
+        ARD = bool(rng.randint(2))
+        ls = rng.uniform(0.3, 2.0, d if ARD else 1)
+        v, noise = float(rng.uniform(0.3, 3.0)), float(10 ** rng.uniform(-3, 0))
+        X, Xs = rng.randn(N, d), rng.randn(17, d)
+        Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.randn(N, 1)
+        st = o.fit(X, Y, name, v, ls, ARD, noise)
+        mean, var = o.predict(st, Xs, include_noise=False)
+        lsk = ls if ARD else float(ls[0])
+        base = RBF(lsk) if name == "GPyRBF" else Matern(lsk, nu=nu[name])
+        gp = GaussianProcessRegressor(kernel=ConstantKernel(v) * base, alpha=noise + 1e-8, optimizer=None).fit(X, Y)
+        ms, ss = gp.predict(Xs, return_std=True)
+        assert normwise(mean[:, 0], ms.ravel()) < TOL, (case, name)
+        assert np.abs(var[:, 0] - ss ** 2).max() < TOL * max(1.0, v), (case, name)
+        lml = gp.log_marginal_likelihood(gp.kernel_.theta)
+        assert abs(st["lml"] - lml) <= TOL * max(1.0, abs(lml)), (case, name)
