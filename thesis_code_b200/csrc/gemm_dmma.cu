@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "gpx_common.cuh"
+#include "tile_walk.cuh"
 
 namespace {
 
@@ -44,7 +45,6 @@ constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStages * 8 + 128;
 #ifndef GPX_WAR_FENCE_MODE
 #define GPX_WAR_FENCE_MODE 1
 #endif
-constexpr int kStrip = 8;                                // output tile columns per rasterisation strip
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -84,46 +84,6 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "+d"(c0), "+d"(c1)
         : "d"(a), "d"(b));
 }
-
-// Output-tile enumeration shared by producer and consumers: strips of kStrip column ordinals, row-major inside a
-// strip, so CTAs running together share few operand panels (L2 reuse).  Invalid (above-diagonal) slots of a
-// triangular job are skipped.  A CTA owns `chunk` consecutive slots; grids larger than the SM count are scheduled
-// by the hardware as earlier CTAs retire, which balances the ragged triangular jobs and lets kernels of other
-// streams (panel factorisation, NCCL) interleave.
-struct TileWalk {
-    int tri, i0, i1, ncols;
-    int strip_m0, strip_w, strip_r0;
-    long long strip_begin, strip_end;
-    __device__ void set_strip(const GemmJob& j) {
-        strip_w = min(kStrip, ncols - strip_m0);
-        strip_r0 = tri ? max(i0, gpx_job_col(j, strip_m0)) : i0;
-        if (strip_r0 > i1) strip_r0 = i1;
-    }
-    __device__ void init(const GemmJob& j) {
-        tri = j.tri; i0 = j.i0; i1 = j.i1; ncols = j.ncols;
-        strip_m0 = 0;
-        set_strip(j);
-        strip_begin = 0;
-        strip_end = (long long)(i1 - strip_r0) * strip_w;
-    }
-    // t counts HALF-tile slots: tile slot t >> 1, row half t & 1.  Returns false when t is past the end.
-    __device__ bool locate(const GemmJob& j, long long t2, int& I, int& J, int& half, bool& valid) {
-        half = (int)(t2 & 1);
-        const long long t = t2 >> 1;
-        while (t >= strip_end) {
-            strip_m0 += strip_w;
-            if (strip_m0 >= ncols) return false;
-            set_strip(j);
-            strip_begin = strip_end;
-            strip_end = strip_begin + (long long)(i1 - strip_r0) * strip_w;
-        }
-        long long u = t - strip_begin;
-        I = strip_r0 + (int)(u / strip_w);
-        J = gpx_job_col(j, strip_m0 + (int)(u % strip_w));
-        valid = !tri || I >= J;
-        return true;
-    }
-};
 
 template <bool kOverwrite>
 __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob job) {
@@ -249,28 +209,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob jo
             gpx_publish_for_async_proxy();
         }
     }
-}
-
-long long count_valid_tiles(const GemmJob& j) {
-    long long total = 0;
-    for (int m = 0; m < j.ncols; m++) {
-        int c = gpx_job_col(j, m);
-        int r0 = j.tri ? (j.i0 > c ? j.i0 : c) : j.i0;
-        if (r0 < j.i1) total += j.i1 - r0;
-    }
-    return total;
-}
-
-long long count_slots(const GemmJob& j) {
-    long long total = 0;
-    for (int m0 = 0; m0 < j.ncols; m0 += kStrip) {
-        int w = (j.ncols - m0 < kStrip) ? (j.ncols - m0) : kStrip;
-        int c0 = gpx_job_col(j, m0);
-        int r0 = j.tri ? (j.i0 > c0 ? j.i0 : c0) : j.i0;
-        if (r0 > j.i1) r0 = j.i1;
-        total += (long long)(j.i1 - r0) * w;
-    }
-    return total;
 }
 
 }  // namespace

@@ -1,0 +1,71 @@
+// Work enumeration of the tile GEMM (csrc/gemm_dmma.cu), kept in a header so that the same code is exercised on the
+// host by tests/test_tilewalk_cpu.py (every valid output tile of a job must be visited exactly once, whatever the grid).
+#pragma once
+#include "gpx_common.cuh"
+
+#define GPX_GEMM_STRIP 8   // output tile columns per rasterisation strip
+
+// Output-tile enumeration shared by producer and consumers: strips of GPX_GEMM_STRIP column ordinals, row-major inside a
+// strip, so CTAs running together share few operand panels (L2 reuse).  Invalid (above-diagonal) slots of a
+// triangular job are skipped.  A CTA owns `chunk` consecutive slots; grids larger than the SM count are scheduled
+// by the hardware as earlier CTAs retire, which balances the ragged triangular jobs and lets kernels of other
+// streams (panel factorisation, NCCL) interleave.
+struct TileWalk {
+    int tri, i0, i1, ncols;
+    int strip_m0, strip_w, strip_r0;
+    long long strip_begin, strip_end;
+    __host__ __device__ void set_strip(const GemmJob& j) {
+        strip_w = (GPX_GEMM_STRIP < ncols - strip_m0 ? GPX_GEMM_STRIP : ncols - strip_m0);
+        strip_r0 = tri ? (i0 > gpx_job_col(j, strip_m0) ? i0 : gpx_job_col(j, strip_m0)) : i0;
+        if (strip_r0 > i1) strip_r0 = i1;
+    }
+    __host__ __device__ void init(const GemmJob& j) {
+        tri = j.tri; i0 = j.i0; i1 = j.i1; ncols = j.ncols;
+        strip_m0 = 0;
+        set_strip(j);
+        strip_begin = 0;
+        strip_end = (long long)(i1 - strip_r0) * strip_w;
+    }
+    // t counts HALF-tile slots: tile slot t >> 1, row half t & 1.  Returns false when t is past the end.
+    __host__ __device__ bool locate(const GemmJob& j, long long t2, int& I, int& J, int& half, bool& valid) {
+        half = (int)(t2 & 1);
+        const long long t = t2 >> 1;
+        while (t >= strip_end) {
+            strip_m0 += strip_w;
+            if (strip_m0 >= ncols) return false;
+            set_strip(j);
+            strip_begin = strip_end;
+            strip_end = strip_begin + (long long)(i1 - strip_r0) * strip_w;
+        }
+        long long u = t - strip_begin;
+        I = strip_r0 + (int)(u / strip_w);
+        J = gpx_job_col(j, strip_m0 + (int)(u % strip_w));
+        valid = !tri || I >= J;
+        return true;
+    }
+};
+
+
+// ---- host-side counters used by the launcher ---------------------------------------------------------------------
+inline long long count_valid_tiles(const GemmJob& j) {
+    long long total = 0;
+    for (int m = 0; m < j.ncols; m++) {
+        int c = gpx_job_col(j, m);
+        int r0 = j.tri ? (j.i0 > c ? j.i0 : c) : j.i0;
+        if (r0 < j.i1) total += j.i1 - r0;
+    }
+    return total;
+}
+
+inline long long count_slots(const GemmJob& j) {
+    long long total = 0;
+    for (int m0 = 0; m0 < j.ncols; m0 += GPX_GEMM_STRIP) {
+        int w = (j.ncols - m0 < GPX_GEMM_STRIP) ? (j.ncols - m0) : GPX_GEMM_STRIP;
+        int c0 = gpx_job_col(j, m0);
+        int r0 = j.tri ? (j.i0 > c0 ? j.i0 : c0) : j.i0;
+        if (r0 > j.i1) r0 = j.i1;
+        total += (long long)(j.i1 - r0) * w;
+    }
+    return total;
+}
+
