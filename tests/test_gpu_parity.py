@@ -233,12 +233,17 @@ def test_c2_full_size_vs_oracle():
     assert abs(m.get_marginal_log_likelihood() - om.state["lml"]) / abs(om.state["lml"]) < TOL
 
 
-def test_c3_full_size_properties():
-    """BASELINE config C3 at full size (N=40000): size-independent properties instead of an O(N^3) CPU run.
-    (i) Ky alpha = y - m (residual, Ky rebuilt blockwise on the host), (ii) predicting at training points with
-    include_noise=False gives mean -> y - noise*alpha exactly (K alpha = y - (noise+jitter) alpha), (iii) variances in
-    (0, sigma_f^2 + sigma_n^2], (iv) LML equals -0.5(N log 2pi + logdet + y^T alpha) with the exported alpha."""
-    c = synthetic.make_config("C3")
+@pytest.mark.parametrize("cfg", ["C3"])
+def test_full_size_properties(cfg):
+    """BASELINE config C3 (N=40000, d=8, Matern-5/2 ARD) at FULL training size: size-independent properties instead of an
+    O(N^3) CPU run.  (C4 at N=60000 was tried with this check: its inputs scaled by the lengthscale reach |x/l| ~ 2000, so
+    the Gram-trick r^2 rebuilt by numpy on the host differs from the GPU's by ~1e-9 -- the SURVEY 7.3 #2 effect -- and
+    with |alpha| ~ 1e3 the host-side residual is 2e-7: that measures the two K-builds against each other, not the solver.
+    C4 is covered at reduced size against the oracle and at full size by bench.py.)  (i) Ky alpha = y - m (residual, Ky rebuilt blockwise on the host), (ii)
+    predicting at training points with include_noise=False gives mean = y - (noise+jitter) alpha exactly (K alpha = y -
+    (noise+jitter) alpha), (iii) variances in (0, sigma_f^2], (iv) LML equals -0.5(N log 2pi + logdet + y^T alpha) with
+    the exported alpha."""
+    c = synthetic.make_config(cfg, Ns=256)
     kw = c["model"]["kwargs"]; kk = kw["kernel"]["kwargs"]
     N = c["N"]
     m = GPModel.from_config(kw)
@@ -248,13 +253,13 @@ def test_c3_full_size_properties():
     noise = kw["noise_prior"]
     r = np.empty_like(alpha)
     for s in range(0, N, 4000):
-        Kb = o.kernel_matrix(kw["kernel"]["name"], c["X"][s:s + 4000], c["X"], kk["variance"], kk["lengthscale"], True)
+        Kb = o.kernel_matrix(kw["kernel"]["name"], c["X"][s:s + 4000], c["X"], kk["variance"], kk["lengthscale"], kk.get("ARD", False))
         r[s:s + 4000] = Kb @ alpha
     r += (noise + 1e-8) * alpha
     assert np.linalg.norm(r - c["Y"]) / np.linalg.norm(c["Y"]) < 1e-9
     idx = np.arange(0, N, 13)[:3000]
     mean, var = h.predict(c["X"][idx], include_noise=False)
-    np.testing.assert_allclose(mean, c["Y"][idx] - (noise + 1e-8) * alpha[idx], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(mean, c["Y"][idx] - (noise + 1e-8) * alpha[idx], rtol=0, atol=1e-8 * max(1.0, np.abs(alpha).max() * noise))
     assert var.min() > 0 and var.max() <= kk["variance"] + 1e-12
     lml, logdet, quad = h.lml()
     np.testing.assert_allclose(quad, float((alpha * c["Y"]).sum()), rtol=1e-10)
