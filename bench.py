@@ -29,6 +29,11 @@ sys.path.insert(0, ROOT)
 
 FP64_DMMA_PEAK_TFLOPS = 36.96   # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.txt)
 METRIC = "exact-GP fit+predict FP64 throughput (algorithmic N^3/3 + N^2*N* flop per fit+predict)"
+# DRAM traffic of the dominant kernel from the latest `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum of
+# one launch; profiles/): refreshed whenever the kernel changes.
+GEMM_TRAFFIC = {"dram_bytes_per_launch": 8.92e9,
+                "note": "ncu --set full capture of one trailing-update launch (profiles/r01_gemm_dmma_ncu_summary.txt): 8.92 GB DRAM "
+                        "for 2.9 GB algorithmic operand bytes (13.7% of HBM peak: the kernel is DMMA-bound)"}
 
 
 def algorithmic_flops(N, Ns):
@@ -110,31 +115,82 @@ def cpu_oracle_step(cfg):
             ctx.restore_original_limits()
 
 
+WORKLOAD_TEXT = {"C4": "1-D natural-sound-shaped exact GP, N=60k, 100k test points",
+                 "C5": "ARD-RBF exact GP d=8, N=200k, block-cyclic Cholesky",
+                 "C3": "Matern-5/2 ARD kin40k-shaped d=8, N=40k",
+                 "C2": "ARD-RBF Genz oscillatory d=10, N=20k",
+                 "C1": "RBF Sinc 1-D, N=1000"}
+FULL_SIZES = {"C1": (1000, 1, 1000), "C2": (20000, 10, 2500), "C3": (40000, 8, 4000), "C4": (60000, 1, 100000), "C5": (200000, 8, 2500)}
+KERNEL_OF = {"C1": "GPyRBF", "C2": "GPyRBF", "C3": "GPyMatern52", "C4": "GPyRBF", "C5": "GPyRBF"}
+
+
+def config_block(workload, N, d, Ns, world):
+    """The `config` object of the JSON line -- identical for the CUDA arm and the reference arm of the same command."""
+    return {"workload": "%s: %s" % (workload, WORKLOAD_TEXT[workload]), "N": N, "d": d, "N_test": Ns, "kernel": KERNEL_OF[workload],
+            "parallelism": "1 GPU" if world == 1 else "block-column-cyclic x%d" % world,
+            "l2_policy": "inputs larger than L2 (factor %.1f GB >> 126 MB)" % (N * (N + 128) / 2 * 8 / 1e9)}
+
+
 def run_reference(args, workload, rank):
     """--impl reference: the reference's CPU implementation of the path.  GPy (where the reference's arithmetic lives)
-    is not installable here, so this times the oracle port with all host BLAS threads on a bounded sample."""
+    is not installable here, so this times the oracle port with all host BLAS threads, each step a BOUNDED SAMPLE of the
+    workload (the same generator at N=12000, N*=2000 unless --N/--Ns say otherwise; full size would take hours on the
+    host), reported in the metric's unit (algorithmic TFLOP/s of that sample)."""
     if rank != 0:
         return
     from thesis_code_b200 import synthetic
+    t_start = time.perf_counter()
+    budget = float(os.environ.get("GPX_BENCH_REF_BUDGET_S", "420"))
     sN, sNs = (args.N or 12000), (args.Ns or 2000)
     cfg = synthetic.make_config(workload, N=sN, Ns=sNs)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_oracle_step(cfg)
-    runs = [cpu_oracle_step(cfg) for _ in range(args.steps)]
+    warm = []
+    for _ in range(max(1, args.warmup)):
+        warm.append(cpu_oracle_step(cfg)[0])
+        if time.perf_counter() - t_start > 0.25 * budget:
+            break
+    runs = []
+    for _ in range(args.steps):
+        runs.append(cpu_oracle_step(cfg))
+        if time.perf_counter() - t_start + runs[-1][0] > budget:
+            break
     t = float(np.mean([r[0] for r in runs]))
     threads = runs[0][1]
     val = algorithmic_flops(cfg["N"], cfg["Ns"]) / t / 1e12
-    sample = "%s generator at N=%d, N*=%d (bounded sample; full size is N=%s)" % (workload, cfg["N"], cfg["Ns"], {"C4": "60000", "C5": "200000"}.get(workload, "?"))
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+    fN, fd, fNs = FULL_SIZES[workload]
+    sample = ("oracle (numpy/scipy port of the GPy path) on the %s generator at N=%d, N*=%d per step (bounded sample; full size "
+              "N=%d, N*=%d would take ~%.0f s per step at this rate)" % (workload, cfg["N"], cfg["Ns"], fN, fNs,
+                                                                      algorithmic_flops(fN, fNs) / (val * 1e12)))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": len(runs),
+            "warmup": len(warm), "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload + " (bounded CPU sample)", "N": cfg["N"], "d": cfg["d"], "N_test": cfg["Ns"]},
-            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": config_block(workload, fN, fd, fNs, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample,
+                             "sample_N": cfg["N"], "sample_N_test": cfg["Ns"]},
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def golden_parity(h, workload, N, kid, variance, ls, noise, ard, torch):
+    """Parity of THIS run's fitted state against the committed full-size golden vectors (tests/golden/
+    exact_gp_golden_large.npz, generated by the oracle's arithmetic on the host): only for a workload / size it holds."""
+    path = os.path.join(ROOT, "tests", "golden", "exact_gp_golden_large.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    if workload + "_N" not in z.files or int(z[workload + "_N"]) != N:
+        return None
+    Xs = np.ascontiguousarray(z[workload + "_Xs"])
+    mean, var = h.predict(Xs, want_var=True, include_noise=True)
+    nrm = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    lml = h.lml()[0]
+    return {"vs": "tests/golden/exact_gp_golden_large.npz (oracle arithmetic at full size)", "test_points": int(Xs.shape[0]),
+            "mean_normwise": nrm(mean, z[workload + "_mean"]), "var_normwise": nrm(var, z[workload + "_var_with_noise"]),
+            "lml_rel": abs(lml - float(z[workload + "_lml"])) / abs(float(z[workload + "_lml"])), "gate": 1e-8}
+
+
 def main():
+    t_proc = time.perf_counter()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -144,6 +200,9 @@ def main():
     ap.add_argument("--N", type=int, default=None)
     ap.add_argument("--Ns", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--budget-s", type=float, default=float(os.environ.get("GPX_BENCH_BUDGET_S", "600")),
+                    help="wall-clock budget of the whole run: the number of full-size timed steps is cut to fit it")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -151,8 +210,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = args.workload or ("C4" if args.gpus == 1 else "C5")
     if args.steps is None:
-        # defaults that finish within minutes: C4 on one GPU is ~13 s / step, C5 (N=200k) is ~45 / 25 / 13 s on 2 / 4 / 8 GPUs
-        args.steps = 3 if args.gpus == 1 else (1 if args.gpus == 2 else 2)
+        # defaults that finish within minutes: C4 on one GPU is ~12.5 s / step, C5 (N=200k) is ~42 / 21 / 11 s on 2 / 4 / 8 GPUs
+        args.steps = 3 if args.gpus == 1 else 2
 
     if args.impl == "reference":
         run_reference(args, workload, rank)
@@ -172,6 +231,7 @@ def main():
     cfg = synthetic.make_config(workload, N=args.N, Ns=args.Ns)
     N, d, Ns = cfg["N"], cfg["d"], cfg["Ns"]
     kid, variance, ls, noise = kernel_args(cfg)
+    ard = bool(cfg["model"]["kwargs"]["kernel"]["kwargs"].get("ARD", False))
     flops = algorithmic_flops(N, Ns)
 
     h = _gpx.Handle(local_rank)
@@ -189,17 +249,40 @@ def main():
     dvar = torch.empty((Ns,), dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
 
-    def device_step():
-        h.fit_device(dX.data_ptr(), N, d, dY.data_ptr(), 1, kid, variance, ls, noise)
-        h.predict_device(dXs.data_ptr(), Ns, dmean.data_ptr(), dvar.data_ptr(), True)
+    def device_step(n=N, ns=Ns):
+        h.fit_device(dX.data_ptr(), n, d, dY.data_ptr(), 1, kid, variance, ls, noise, ARD=ard)
+        h.predict_device(dXs.data_ptr(), ns, dmean.data_ptr(), dvar.data_ptr(), True)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        device_step()
+    def agree(x, op):   # every rank must take the same decisions about step counts
+        if dist is None:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    # ---- warm-up: W-1 steps on a prefix of the same data (kernels, NCCL communicators, streams: < 1 s each), then ONE at
+    # full size (allocation of the factor, page faults) whose wall time also sizes the timed region to the budget
+    warm_small_n = min(N, 16384)
+    n_small = max(0, args.warmup - 1)
+    for _ in range(n_small):
+        device_step(warm_small_n, min(Ns, 4096))
+    barrier()
+    t0 = time.perf_counter()
+    device_step()
+    barrier()
+    t_full = agree(time.perf_counter() - t0, dist.ReduceOp.MAX if dist is not None else None)
+    warm_done = n_small + 1
+    e2e_steps = 1 if t_full > 20.0 else max(1, min(args.steps, 2))
+    cpu_reserve = 0.0 if (args.no_cpu_baseline or rank != 0) else 25.0
+    check_reserve = 0.0 if args.no_check else 0.15 * t_full + 10.0
+    left = args.budget_s - (time.perf_counter() - t_proc) - e2e_steps * 1.05 * t_full - cpu_reserve - check_reserve - 20.0
+    steps = int(agree(max(1, min(args.steps, int(left / t_full))), dist.ReduceOp.MIN if dist is not None else None))
+
     h.gemm_stats()
     launches0 = h.launch_count()
     sampler = ClockSampler(local_rank)
@@ -208,7 +291,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase_acc = {}
     e0.record(ext)
-    for _ in range(args.steps):
+    for i in range(steps):
         device_step()
         for k, v in h.phase_ms().items():
             phase_acc[k] = phase_acc.get(k, 0.0) + v
@@ -222,9 +305,28 @@ def main():
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = flops / (ms_step * 1e-3) / 1e12
-    phases = {k: v / args.steps for k, v in phase_acc.items()}
+    phases = {k: v / steps for k, v in phase_acc.items()}
+
+    # ---- self-check of the state the timed steps left behind (outside the timed region, on the device) --------------------
+    check = None
+    if not args.no_check:
+        check = h.selfcheck()          # collective when sharded
+        check["var_min"] = float(dvar.min().item())
+        check["var_max"] = float(dvar.max().item())
+        lml = h.lml()[0]
+        check["lml"] = lml
+        if dist is not None:
+            t = torch.tensor([lml, -lml], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            check["lml_spread_over_ranks"] = float(t[0].item() + t[1].item())
+        else:
+            gp = golden_parity(h, workload, N, kid, variance, ls, noise, ard, torch)
+            if gp is not None:
+                check["golden_parity"] = gp
+        check["what"] = ("solve_residual = ||Ky alpha - y|| / ||y||, factor_residual = ||L L^T v - Ky v|| / ||Ky v|| with Ky rebuilt "
+                         "tile-wise by the K-build kernels; var_min / var_max over all test points of the last timed step")
 
     # ---- e2e: the public GPModel API with host numpy buffers (H2D + D2H inside the timed region) ----------------
     model = GPModel.from_config(cfg["model"]["kwargs"])
@@ -232,7 +334,6 @@ def main():
     model._handle = h          # same handle: the NCCL communicator (world > 1) is already set up
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = 1 if world > 1 else max(1, min(args.steps, 2))   # a sharded N=200k step is 11-42 s: one is enough
     for _ in range(e2e_steps):
         model.init(cfg["X"], cfg["Y"])
         mean, var = model.get_statistics(cfg["Xs"], full_cov=False)
@@ -262,14 +363,13 @@ def main():
     peaks = measured_peaks()
     roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA tile GEMM)", "achieved": achieved,
                 "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": (achieved / FP64_DMMA_PEAK_TFLOPS) if achieved else None,
-                "traffic": None,
+                "traffic": GEMM_TRAFFIC["dram_bytes_per_launch"],
                 "peak_source": "fallback: MEASURED_PEAKS.json has no FP64 figure; 36.96 TFLOP/s = register-resident "
                                "mma.sync.m8n8k4.f64 loop measured on this pool's B200 (profiles/r01_fp64_peak.txt)",
-                "gemm_launches": gemm_launches, "gemm_ms_per_step": gemm_ms / args.steps,
-                "timed_flops_share_of_step": gemm_issued / (flops * args.steps / max(world, 1)),
+                "gemm_launches": gemm_launches, "gemm_ms_per_step": gemm_ms / steps,
+                "timed_flops_share_of_step": gemm_issued / (flops * steps / max(world, 1)),
                 "per_gpu": world > 1,
-                "traffic_note": "one ncu --set full capture of this kernel (profiles/r01_gemm_dmma_ncu_summary.txt): 5.60 GB "
-                                "DRAM for a launch with 2.97 GB algorithmic bytes (12% of HBM peak; the kernel is DMMA-bound)",
+                "traffic_note": GEMM_TRAFFIC["note"],
                 "kernel_share_of_step": gemm_ms / ms_total if ms_total > 0 else None}
 
     # ---- CPU baseline: oracle port on a bounded sample ------------------------------------------------------------
@@ -281,17 +381,13 @@ def main():
         cpu = {"value": algorithmic_flops(sN, sNs) / t / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": "port",
                "sample": "oracle (numpy/scipy port of the GPy path) on the %s generator at N=%d, N*=%d: %.1f s" % (workload, sN, sNs, t)}
 
-    line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm_done,
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "warmup_detail": "%d on the first %d training rows, then 1 at full size" % (n_small, warm_small_n),
+            "budget_s": args.budget_s, "wall_s": time.perf_counter() - t_proc,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (workload, {"C4": "1-D natural-sound-shaped exact GP, N=60k, 100k test points",
-                                                           "C5": "ARD-RBF exact GP d=8, N=200k, block-cyclic Cholesky",
-                                                           "C3": "Matern-5/2 ARD kin40k-shaped d=8, N=40k",
-                                                           "C2": "ARD-RBF Genz oscillatory d=10, N=20k",
-                                                           "C1": "RBF Sinc 1-D, N=1000"}[workload]),
-                       "N": N, "d": d, "N_test": Ns, "kernel": cfg["model"]["kwargs"]["kernel"]["name"],
-                       "parallelism": "1 GPU" if world == 1 else "block-column-cyclic x%d" % world,
-                       "l2_policy": "inputs larger than L2 (factor %.1f GB >> 126 MB)" % (N * (N + 128) / 2 * 8 / 1e9)},
+            "config": config_block(workload, N, d, Ns, world),
             "fit_predict_sec": ms_step * 1e-3, "cholesky_tflops": chol_tflops,
             "cholesky_frac_of_fp64_peak": chol_tflops / FP64_DMMA_PEAK_TFLOPS / max(world, 1),
             "variance_trsm_tflops": trsm_tflops, "phase_ms": phases,
@@ -303,9 +399,10 @@ def main():
             "backward_solve_gbs": (8.0 * N * (N + 1) / 2 / max(world, 1)) / (phases["solve"] * 1e-3) / 1e9,
             "kstar_gevals_per_s": (float(N) * Ns / max(world, 1)) / (phases["predict_kstar"] * 1e-3) / 1e9 if phases.get("predict_kstar", 0) > 0 else None,
             "hbm_peak_gbs": peaks.get("hbm_gbs"),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "check": check,
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "api": "GPModel.init(X, Y) + get_statistics(Xtest, full_cov=False) on numpy arrays"},
+                    "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "api": "GPModel.init(X, Y) + get_statistics(Xtest, full_cov=False) on numpy arrays"},
             "gpu_launches": launches, "clocks": sampler.summary()}
     print(json.dumps(line), flush=True)
     if dist is not None:

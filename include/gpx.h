@@ -10,8 +10,13 @@
  *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
  *   - every array argument is float64, C-contiguous (row-major), exactly as GPModel receives numpy arrays
  *     (src/models/core_models.py:58-63, 185-187).
- *   - `mem` says where the caller's buffers live: GPX_MEM_HOST (numpy arrays; the library stages them through
- *     pinned memory on its stream) or GPX_MEM_DEVICE (pointers into this handle's GPU, e.g. torch tensors).
+ *   - `mem` says where the caller's buffers live: GPX_MEM_HOST (numpy arrays, copied with cudaMemcpyAsync on the
+ *     handle's stream; the small-batch predict path stages through a persistent pinned buffer) or GPX_MEM_DEVICE
+ *     (pointers into this handle's GPU, e.g. torch tensors).
+ *   - streams: every call runs on the handle's own streams and returns after they have drained, so results are
+ *     visible to any stream afterwards.  Device inputs produced on another stream must be ordered BEFORE the call:
+ *     either synchronise that stream or hand it to gpx_set_stream(), after which every call first waits (on the
+ *     device, via an event) for the work already enqueued there.
  *   - return 0 = OK; > 0 = LAPACK-style info (1-based index of the first non-positive pivot of Ky, cf. GPy
  *     util.linalg.jitchol, which the Python layer mimics by retrying with more jitter); < 0 = bad argument /
  *     CUDA / NCCL error, text in gpx_last_error().  No exceptions cross the ABI.
@@ -64,14 +69,41 @@ GPX_API int gpx_comm_init(gpx_t* h, int rank, int world, const char* uid128);
  * src/models/core_models.py:201-209, i.e. ExactGaussianInference.inference:
  *     Ky = K(X,X) + (noise + jitter) I ;  L = chol(Ky) (lower) ;  alpha = Ky^-1 (Y - mean_const) ;
  *     logdet = 2 sum log L_ii ;  LML = 0.5 (-N O log 2pi - O logdet - sum(alpha * (Y - mean_const))).
- * X is (N, d), Y is (N, O).  `lengthscale` has n_ls = 1 (isotropic) or d (ARD) entries
- * (kernel kwargs `variance`, `lengthscale`, `ARD` of the config dict, core_models.py:167-174,192).
+ * X is (N, d), Y is (N, O).  `ard` is the kernel kwarg `ARD` (core_models.py:167-174,192): 1 -> `lengthscale` has
+ * n_ls = d entries and the inputs are divided by them BEFORE the Gram-trick distance; 0 -> n_ls = 1 and the distance of
+ * the unscaled inputs is divided by it AFTERWARDS -- GPy's Stationary._scaled_dist, operation for operation (the two
+ * orders differ by ~1e-9 in r^2 when |x / l| is large).
  * `noise` = Gaussian_noise.variance; `jitter` = GPy's fixed 1e-8; `mean_const` = mean(Y) when the config sets
  * mean_prior (core_models.py:194-196), else 0.
  */
 GPX_API int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O, int kernel_id,
-            double variance, const double* lengthscale, int n_ls, double noise, double jitter,
+            double variance, const double* lengthscale, int n_ls, int ard, double noise, double jitter,
             double mean_const, int mem);
+
+/*
+ * Fused NormalizerModel (src/models/normalizer.py:36-48,51-114; notebook_header.py:17-26 wraps every model in it).
+ * After gpx_set_normalizer(h, nx, ny) every gpx_fit computes the column means / population standard deviations of the
+ * raw X (nx) and Y (ny) on the device, z-scores X in the input loader of the K-build and Y in the residual kernel, and
+ * every predict z-scores the test inputs in its loader and de-normalises in its epilogue (mean * std_y + mean_y,
+ * var * std_y^2) -- no normalised copy of the data exists on the host.  gpx_get_normalizer returns the statistics of
+ * the last fit (any pointer may be NULL; x_* have d entries, y_* have O).
+ */
+GPX_API int gpx_set_normalizer(gpx_t* h, int normalize_input, int normalize_output);
+GPX_API int gpx_get_normalizer(gpx_t* h, double* x_mean, double* x_std, double* y_mean, double* y_std);
+
+/* Order every later call after the work already enqueued on `stream` (a cudaStream_t; NULL = the legacy default
+ * stream; call with has_stream = 0 to switch the waiting off again). */
+GPX_API int gpx_set_stream(gpx_t* h, void* stream, int has_stream);
+
+/*
+ * APPEND k observations to the fitted model without refactorising (single-GPU handles, no normaliser): the new rows
+ * of K are built, solved against the resident factor (the same DMMA triangular solve as the predictive variance), the
+ * k x k Schur complement is factored, alpha and the LML are recomputed by two O(N^2) substitutions.  O(k N^2) instead
+ * of the O(N^3) refit that BaseModel.add_observations performs (src/models/core_models.py:65-77; called once per
+ * Bayesian-optimisation step from src/algorithms.py:120-143).  Returns 0, > 0 (non-positive pivot: the caller refits
+ * with jitter), -8 when the handle cannot append (sharded / normalised: the caller refits).
+ */
+GPX_API int gpx_append(gpx_t* h, const double* X_new, int64_t k, const double* Y_new, int mem);
 
 /* log marginal likelihood / log-determinant / quadratic form of the last fit (host scalars).
  * Replaces gpy_model.log_likelihood() (name from MarginalLogLikelihoodMixin, core_models.py:12-14). */
@@ -82,9 +114,16 @@ GPX_API int gpx_lml(gpx_t* h, double* lml, double* logdet, double* quad);
  * GPModel._predict (src/models/core_models.py:249-263, 270-271):
  *     mean[j, o] = sum_i k(x_i, x*_j) alpha[i, o] + mean_const
  *     var[j]     = variance - sum_i T_ij^2 + (include_noise ? noise : 0),   T = L^-1 K(X, X*)
- * Xs is (Ns, d); mean is (Ns, O); var is (Ns) or NULL to skip the variance pass.
+ * Xs is (Ns, d); mean is (Ns, O); var is NULL (skip the variance pass), (Ns) with var_cols = 1 (GPy: one variance
+ * shared by all outputs) or (Ns, O) with var_cols = O (required when the output normaliser is on and O > 1: each
+ * output's variance is scaled by its own std^2).
+ * Ns <= 128 on a single-GPU handle takes the latency path (src/growth_model_GPR/ipopt_wrapper.py:55 and
+ * src/acquisition_functions.py:38,79 predict one or a few rows at a time, by the million): persistent workspaces and a
+ * pinned staging buffer (no allocation, no cudaMemGetInfo), the variance of <= 8 rows by GEMV-style forward
+ * substitution (L is read once, no tensor-core tile work), the whole launch chain replayed as a CUDA graph.
  */
-GPX_API int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int include_noise, int mem);
+GPX_API int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int var_cols,
+                int include_noise, int mem);
 
 /* Full predictive covariance (Ns x Ns, row-major) for small Ns: core_models.py:244-259 (`full_cov=True`). */
 GPX_API int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* cov, int include_noise,
@@ -98,13 +137,33 @@ GPX_API int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean
  */
 GPX_API int gpx_lml_grad(gpx_t* h, double* grad, int capacity);
 
+/*
+ * Moments of the posterior mean for its Jacobian / Hessian (GPModel.predict_jacobian / predict_hessian,
+ * src/models/core_models.py:313-380, consumed by src/acquisition_functions.py:86,113), first output only like the
+ * reference.  With w_ji = k(x_j, x*_i) alpha_j and dx_jik = x*_ik - x_jk in the coordinates the kernel sees
+ * (z-scored / ARD-scaled if applicable):
+ *     S0[i] = sum_j w_ji,   S1[i][k] = sum_j w_ji dx_jik,   S2[i][k][l] = sum_j w_ji dx_jik dx_jil  (NULL to skip).
+ * The host layer turns them into the reference's expressions.  Fixed summation order (deterministic).
+ */
+GPX_API int gpx_predict_moments(gpx_t* h, const double* Xs, int64_t Ns, double* S0, double* S1, double* S2, int mem);
+
+/*
+ * Self-check of the fitted state on the device (bench.py prints it; SURVEY.md section 8(d) "Parity check"): with Ky
+ * rebuilt tile by tile from the inputs (never stored),
+ *     out[0] = || Ky alpha - (y - m) ||_2 / || y - m ||_2          (the solve)
+ *     out[1] = || L (L^T v) - Ky v ||_2 / || Ky v ||_2              (the factor; v = fixed pseudo-random vector)
+ *     out[2] = || Ky v ||_2,  out[3] = || y - m ||_2.
+ * Collective on a sharded handle (every rank calls it; every rank gets the same numbers).
+ */
+GPX_API int gpx_selfcheck(gpx_t* h, double* out, int capacity);
+
 /* Export for pickling / tests: alpha (N x O row-major) and, if L != NULL, the dense row-major lower factor
  * (N x N, upper triangle zeroed; only sensible for small N).  Host buffers. */
 GPX_API int gpx_export(gpx_t* h, double* alpha, double* L);
 /* Export K(X,X)+(noise+jitter)I as built by the K-build kernel (before factorisation), dense row-major, small N
  * only: builds into scratch, does not disturb the fitted state.  Host buffer.  Used by the parity tests. */
 GPX_API int gpx_kernel_matrix(gpx_t* h, const double* X, int64_t N, int d, const double* X2, int64_t M, int kernel_id,
-                      double variance, const double* lengthscale, int n_ls, double diag_add, double* K_out);
+                      double variance, const double* lengthscale, int n_ls, int ard, double diag_add, double* K_out);
 
 /* Timing of the last fit / predict, per phase, measured with CUDA events on the handle's stream (ms). */
 GPX_API double gpx_phase_ms(const gpx_t* h, int phase);
@@ -117,7 +176,8 @@ GPX_API int64_t gpx_launch_count(const gpx_t* h);
  * factor / communication / update streams), "gemm_max_chunk" (cap on tile slots per CTA), "group_panels" (panels per delayed far update when sharded, default 1),
  * "nccl_lo_ctas" (CTA cap of the factorisation communicator, default 4; before gpx_comm_init), "cache_mb" (sharded
  * handles keep received panels resident for later predicts: -1 = as many as fit beside a reserve, 0 = none, else a cap
- * in MB), "trace" (see gpx_trace). */
+ * in MB), "trace" (see gpx_trace), "reserve_rows" (row capacity laid out beyond N at fit time so that gpx_append works in
+ * place; single GPU), "predict_graph" (1, default: replay the small-batch predict launch chain as a CUDA graph). */
 GPX_API int gpx_set_option(gpx_t* h, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel of this handle is launched on, so that a caller can
  * bracket calls with its own CUDA events (bench.py does, via torch.cuda.ExternalStream). */
@@ -134,6 +194,13 @@ GPX_API int gpx_gemm_stats(gpx_t* h, double* total_ms, double* issued_flops, int
 GPX_API int64_t gpx_trace(const gpx_t* h, double* out, int64_t capacity);
 /* Device-memory footprint in bytes of the current fit (factor + workspaces). */
 GPX_API int64_t gpx_bytes_allocated(const gpx_t* h);
+
+#ifdef GPX_ENABLE_DEBUG_API
+/* Development aids (tools/gemm_bench.py), only exported when the library is built with `make DEBUG_API=1`:
+ * isolated timing of the DMMA tile GEMM (ms per launch) and of the diagonal-tile POTRF+inverse kernel (us). */
+GPX_API double gpx_debug_gemm(gpx_t* h, int rows, int cols, int ktiles, int overwrite, int max_chunk, int reps);
+GPX_API double gpx_debug_potrf(gpx_t* h, int reps);
+#endif
 
 #ifdef __cplusplus
 }

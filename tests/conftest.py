@@ -46,3 +46,31 @@ def gpu_handle():
     h = _gpx.Handle(0)
     yield h
     h.close()
+
+
+def load_reference_pinned():
+    """tests/golden/reference_pinned.npz: outputs of REFERENCE code executed in the build container
+    (tests/golden/make_golden_reference.py): {tag: {field: array}} for the GPVanillaModel cases v0..v2 and the
+    NormalizerModel<GPVanillaModel> cases n0..n2."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_pinned.npz"))
+    cases = {}
+    for k in z.files:
+        tag, field = k.split("_", 1)
+        cases.setdefault(tag, {})[field] = z[k]
+    return cases
+
+
+@pytest.fixture(scope="session")
+def reference_pinned():
+    return load_reference_pinned()
+
+
+@pytest.fixture(scope="session")
+def golden_large():
+    path = os.path.join(ROOT, "tests", "golden", "exact_gp_golden_large.npz")
+    z = np.load(path)
+    out = {}
+    for k in z.files:
+        tag, field = k.split("_", 1)
+        out.setdefault(tag, {})[field] = z[k]
+    return out

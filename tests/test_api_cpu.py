@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "gpx.h")).read()
+    text = re.sub(r"#ifdef GPX_ENABLE_DEBUG_API.*?#endif", "", text, flags=re.S)    # development aids: `make DEBUG_API=1` only
     return sorted(set(re.findall(r"GPX_API[^;(]*?\b(gpx_\w+)\s*\(", text)))
 
 
@@ -112,31 +113,43 @@ def test_synthetic_configs_shapes_and_determinism():
     assert c["X"].min() >= -20 and c["X"].max() <= 20
 
 
-def test_normalizer_model_wraps_any_model(tmp_path):
-    """NormalizerModel (reference src/models/normalizer.py:51-158) with a stub inner model: z-scoring in, affine map out."""
-    class Stub(pkg.BaseModel):
-        def _fit(self, X, Y, Y_dir=None):
-            self.seen = (X.copy(), Y.copy())
-
-        def _get_statistics(self, X, full_cov=True):
-            mean = np.ones((1, X.shape[0], 1)) * 0.5
-            return mean, (np.ones((1, X.shape[0], X.shape[0], 1)) if full_cov else np.full((1, X.shape[0], 1), 2.0))
-    rng = np.random.RandomState(0)
-    X = rng.rand(50, 3) * 10 + 4; Y = rng.randn(50, 1) * 3 + 7
-    m = pkg.NormalizerModel(Stub())
-    m.init(X, Y)
-    Xn, Yn = m.model.seen
-    np.testing.assert_allclose(Xn.mean(0), 0, atol=1e-12); np.testing.assert_allclose(Xn.std(0), 1, rtol=1e-12)
-    np.testing.assert_allclose(Yn.mean(0), 0, atol=1e-12); np.testing.assert_allclose(Yn.std(0), 1, rtol=1e-12)
-    mean, var = m.get_statistics(X[:5], full_cov=False)
-    np.testing.assert_allclose(mean, np.full((1, 5, 1), 0.5 * Y.std(0)[0] + Y.mean(0)[0]))
-    np.testing.assert_allclose(var, np.full((1, 5, 1), 2.0 * Y.std(0)[0] ** 2))
-    mean, cov = m.get_statistics(X[:5], full_cov=True)
-    assert cov.shape == (1, 5, 5, 1, 1)                          # the reference's trailing-axis quirk is kept
-    assert m.X is X and m.Y is Y
-    nm = pkg.NormalizerModel.from_config({"model": {"name": "GPModel", "kwargs": {"kernel": {"name": "GPyRBF"}, "noise_prior": 0.1}},
-                                          "normalize_output": False})
+def test_normalizer_model_contract_without_gpu(tmp_path):
+    """NormalizerModel (reference src/models/normalizer.py:51-158): constructor / config contract, flags handed to the
+    wrapped GPModel (the z-scores themselves run inside gpx_fit / gpx_predict: GPU tests), pickle layout."""
+    inner = {"name": "GPModel", "kwargs": {"kernel": {"name": "GPyRBF"}, "noise_prior": 0.1}}
+    nm = pkg.NormalizerModel.from_config({"model": inner, "normalize_output": False})
     assert isinstance(nm.model, pkg.GPModel) and nm._normalize_input and not nm._normalize_output
+    assert nm.model._normalize_input and not nm.model._normalize_output          # pushed down: the fit will z-score X only
+    nm2 = pkg.NormalizerModel.from_config({"model": inner})
+    assert nm2.model._normalize_input and nm2.model._normalize_output and nm2.X is None
+    with pytest.raises(AssertionError):
+        nm2.add_observations(np.zeros((1, 1)), np.zeros((1, 1)))                 # "Call init first"
+    with pytest.raises(TypeError):
+        pkg.NormalizerModel(object())                                            # nothing to fuse into
+    nm2.save(str(tmp_path / "nm"))                                               # model.pickle + model/model.pickle
+    assert os.path.isfile(tmp_path / "nm" / "model.pickle") and os.path.isfile(tmp_path / "nm" / "model" / "model.pickle")
+    nm3 = pkg.NormalizerModel.load(str(tmp_path / "nm"))
+    assert isinstance(nm3.model, pkg.GPModel) and nm3.model._normalize_output and nm3._X is None
+    n = pkg.Normalizer(np.array([1.0, 2.0]), np.array([2.0, 4.0]))               # reference helper semantics (:9-33)
+    np.testing.assert_allclose(n.normalize(np.array([[3.0, 6.0]])), [[1.0, 1.0]])
+    np.testing.assert_allclose(n.denormalize(np.array([[1.0, 1.0]])), [[3.0, 6.0]])
+    np.testing.assert_allclose(n.denormalize_variance(np.array([[1.0, 1.0]])), [[4.0, 16.0]])
+    assert n.denormalize_covariance(np.ones((1, 5, 5, 1))).shape == (1, 5, 5, 1, 2)   # the reference's trailing-axis quirk
+
+
+def test_sharding_is_opt_in(monkeypatch):
+    m = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "noise_prior": 0.1})
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    monkeypatch.delenv("GPX_DISTRIBUTED", raising=False)
+    assert not m._wants_sharding()                      # a torchrun sweep of independent models must not meet in a collective
+    monkeypatch.setenv("GPX_DISTRIBUTED", "1")
+    assert m._wants_sharding()
+    m.distributed = False
+    assert not m._wants_sharding()
+    from thesis_code_b200 import distributed as gd
+    a = gd.problem_fingerprint(np.zeros((5, 2)), np.zeros((5, 1)), np.array([1.0, 2.0]))
+    b = gd.problem_fingerprint(np.zeros((5, 2)), np.zeros((5, 1)), np.array([1.0, 2.5]))
+    assert a.shape == (6,) and np.array_equal(a[:5], b[:5]) and a[5] != b[5]
 
 
 def test_committed_bench_lines_follow_the_contract():

@@ -26,6 +26,7 @@ for cfg, N, Ns, W, M, cache in [("C5", 5000, 1000, 4, 1, -1), ("C5", 5000, 1000,
     c = synthetic.make_config(cfg, N=N, Ns=Ns)
     kw = c["model"]["kwargs"]
     m = GPModel.from_config(kw); m.device = lr
+    m.distributed = True                     # sharding is opt-in
     h = m._get_handle()                      # picks the torch.distributed group up and shards the factor
     assert h.world == dist.get_world_size()
     h.set_option("outer_tiles", W)
@@ -41,6 +42,20 @@ for cfg, N, Ns, W, M, cache in [("C5", 5000, 1000, 4, 1, -1), ("C5", 5000, 1000,
     t = torch.from_numpy(np.concatenate([mean.ravel(), var.ravel()])).cuda()
     ref = t.clone(); dist.broadcast(ref, src=0)
     assert bool((t == ref).all())
+    chk = h.selfcheck()                      # collective: residual of the solve and of the sharded factor, on the device
+    assert chk["factor_residual"] < 1e-12 and chk["solve_residual"] < 1e-7, (cfg, chk)
+# a sharded fit is a collective over identical inputs: different data on the ranks must raise, not hang
+c = synthetic.make_config("C2", N=600, Ns=10)
+m = GPModel.from_config(c["model"]["kwargs"]); m.device = lr; m.distributed = True
+try:
+    m.init(c["X"] + (1e-3 if rank == 1 else 0.0), c["Y"])
+    raise SystemExit("fingerprint mismatch was not detected")
+except Exception as e:
+    assert "different data" in str(e), e
+# ... and independent per-rank models (the reference's sweep style) stay independent
+m = GPModel.from_config(c["model"]["kwargs"]); m.device = lr; m.distributed = False
+m.init(c["X"][: 300 + 100 * rank], c["Y"][: 300 + 100 * rank])
+assert m._get_handle().lml()[0] != 0 and getattr(m._get_handle(), "world", 1) == 1
 dist.destroy_process_group()
 print("OK", rank)
 """

@@ -33,6 +33,10 @@ class NotPositiveDefiniteError(np.linalg.LinAlgError):
         self.info = info
 
 
+class AppendUnsupported(RuntimeError):
+    """gpx_append returned -8: this handle cannot append in place (sharded or normalised); the caller refits."""
+
+
 # every symbol include/gpx.h declares: (restype, argtypes)
 SIGNATURES = {
     "gpx_version": (ctypes.c_int, []),
@@ -42,18 +46,25 @@ SIGNATURES = {
     "gpx_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
     "gpx_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
     "gpx_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
-                               ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p, ctypes.c_int,
+                               ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p, ctypes.c_int, ctypes.c_int,
                                ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
+    "gpx_set_normalizer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "gpx_get_normalizer": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p, _c_double_p]),
+    "gpx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "gpx_append": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]),
+    "gpx_predict_moments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "gpx_selfcheck": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int]),
     "gpx_lml": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, _c_double_p, _c_double_p]),
     "gpx_lml_grad": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int]),
     "gpx_predict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
-                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "gpx_predict_cov": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "gpx_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "gpx_kernel_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
-                                         _c_double_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]),
+                                         _c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]),
     "gpx_phase_ms": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_int]),
     "gpx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "gpx_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
@@ -127,24 +138,57 @@ class Handle:
         self._check(self.lib.gpx_comm_init(self._h, int(rank), int(world), uid))
         self.rank, self.world = int(rank), int(world)
 
-    # ---- host (numpy) entry points -----------------------------------------------------------------------
-    def fit(self, X, Y, kernel_id, variance, lengthscale, noise, jitter=1e-8, mean_const=0.0):
-        X, Y = _f64(X), _f64(Y)
+    def set_normalizer(self, normalize_input, normalize_output):
+        """Fused NormalizerModel: z-score X / Y on the device in every later fit, de-normalise in every predict."""
+        self._check(self.lib.gpx_set_normalizer(self._h, int(bool(normalize_input)), int(bool(normalize_output))))
+
+    def get_normalizer(self, d, O):
+        """(x_mean, x_std, y_mean, y_std) of the last fit (zeros / ones where a z-score is off)."""
+        xm, xs, ym, ys = np.zeros(d), np.ones(d), np.zeros(O), np.ones(O)
+        self._check(self.lib.gpx_get_normalizer(self._h, xm.ctypes.data_as(_c_double_p), xs.ctypes.data_as(_c_double_p),
+                                                ym.ctypes.data_as(_c_double_p), ys.ctypes.data_as(_c_double_p)))
+        return xm, xs, ym, ys
+
+    def set_stream(self, stream_ptr):
+        """Order every later call after the work already enqueued on this cudaStream_t (None switches it off)."""
+        self._check(self.lib.gpx_set_stream(self._h, stream_ptr or None, 0 if stream_ptr is None else 1))
+
+    @staticmethod
+    def _ard(lengthscale, d, ARD):
+        """ARD flag for the ABI: explicit, or inferred from the lengthscale count (d == 1 with one value: isotropic)."""
         ls = _f64(np.atleast_1d(lengthscale))
+        if ARD is None:
+            ARD = ls.size > 1
+        if ARD and ls.size == 1 and d > 1:
+            ls = np.full(d, ls[0])
+        return ls, int(bool(ARD))
+
+    # ---- host (numpy) entry points -----------------------------------------------------------------------
+    def fit(self, X, Y, kernel_id, variance, lengthscale, noise, jitter=1e-8, mean_const=0.0, ARD=None):
+        X, Y = _f64(X), _f64(Y)
         N, d = X.shape
+        ls, ard = self._ard(lengthscale, d, ARD)
         assert Y.shape[0] == N and Y.ndim == 2
         rc = self.lib.gpx_fit(self._h, X.ctypes.data, N, d, Y.ctypes.data, Y.shape[1], int(kernel_id), float(variance),
-                              ls.ctypes.data_as(_c_double_p), ls.size, float(noise), float(jitter), float(mean_const),
+                              ls.ctypes.data_as(_c_double_p), ls.size, ard, float(noise), float(jitter), float(mean_const),
                               MEM_HOST)
         self._check(rc)
 
-    def predict(self, Xs, want_var=True, include_noise=True, output_dim=1):
+    def append(self, X_new, Y_new):
+        """Rank-k append to the resident factor (gpx_append).  Raises AppendUnsupported when the handle cannot."""
+        X_new, Y_new = _f64(X_new), _f64(Y_new)
+        rc = self.lib.gpx_append(self._h, X_new.ctypes.data, X_new.shape[0], Y_new.ctypes.data, MEM_HOST)
+        if rc == -8:
+            raise AppendUnsupported(self.lib.gpx_last_error(self._h).decode("utf-8", "replace"))
+        self._check(rc)
+
+    def predict(self, Xs, want_var=True, include_noise=True, output_dim=1, var_cols=1):
         Xs = _f64(Xs)
         Ns = Xs.shape[0]
         mean = np.empty((Ns, output_dim), dtype=np.float64)
-        var = np.empty((Ns,), dtype=np.float64) if want_var else None
+        var = np.empty((Ns,) if var_cols == 1 else (Ns, var_cols), dtype=np.float64) if want_var else None
         rc = self.lib.gpx_predict(self._h, Xs.ctypes.data, Ns, mean.ctypes.data,
-                                  var.ctypes.data if want_var else None, int(bool(include_noise)), MEM_HOST)
+                                  var.ctypes.data if want_var else None, int(var_cols), int(bool(include_noise)), MEM_HOST)
         self._check(rc)
         return mean, var
 
@@ -158,16 +202,33 @@ class Handle:
         self._check(rc)
         return mean, cov
 
+    def predict_moments(self, Xs, order=2):
+        """S0 (Ns), S1 (Ns, d), S2 (Ns, d, d) of gpx_predict_moments (S2 only for order 2)."""
+        Xs = _f64(Xs)
+        Ns, d = Xs.shape
+        S0 = np.empty(Ns); S1 = np.empty((Ns, d)); S2 = np.empty((Ns, d, d)) if order >= 2 else None
+        self._check(self.lib.gpx_predict_moments(self._h, Xs.ctypes.data, Ns, S0.ctypes.data, S1.ctypes.data,
+                                                 S2.ctypes.data if S2 is not None else None, MEM_HOST))
+        return S0, S1, S2
+
+    def selfcheck(self):
+        """dict(residual, factor, kv_norm, y_norm) of gpx_selfcheck (collective on a sharded handle)."""
+        out = np.zeros(4)
+        self._check(self.lib.gpx_selfcheck(self._h, out.ctypes.data_as(_c_double_p), 4))
+        return {"solve_residual": float(out[0]), "factor_residual": float(out[1]), "kv_norm": float(out[2]), "y_norm": float(out[3])}
+
     # ---- device-pointer entry points (inputs already resident in HBM, e.g. torch tensors) -------------------
-    def fit_device(self, X_ptr, N, d, Y_ptr, O, kernel_id, variance, lengthscale, noise, jitter=1e-8, mean_const=0.0):
-        ls = _f64(np.atleast_1d(lengthscale))
+    def fit_device(self, X_ptr, N, d, Y_ptr, O, kernel_id, variance, lengthscale, noise, jitter=1e-8, mean_const=0.0,
+                   ARD=None):
+        ls, ard = self._ard(lengthscale, d, ARD)
         rc = self.lib.gpx_fit(self._h, X_ptr, int(N), int(d), Y_ptr, int(O), int(kernel_id), float(variance),
-                              ls.ctypes.data_as(_c_double_p), ls.size, float(noise), float(jitter), float(mean_const),
+                              ls.ctypes.data_as(_c_double_p), ls.size, ard, float(noise), float(jitter), float(mean_const),
                               MEM_DEVICE)
         self._check(rc)
 
-    def predict_device(self, Xs_ptr, Ns, mean_ptr, var_ptr, include_noise=True):
-        rc = self.lib.gpx_predict(self._h, Xs_ptr, int(Ns), mean_ptr, var_ptr, int(bool(include_noise)), MEM_DEVICE)
+    def predict_device(self, Xs_ptr, Ns, mean_ptr, var_ptr, include_noise=True, var_cols=1):
+        rc = self.lib.gpx_predict(self._h, Xs_ptr, int(Ns), mean_ptr, var_ptr, int(var_cols), int(bool(include_noise)),
+                                  MEM_DEVICE)
         self._check(rc)
 
     # ---- results ------------------------------------------------------------------------------------------
@@ -190,10 +251,10 @@ class Handle:
         self._check(self.lib.gpx_export(self._h, alpha.ctypes.data, L.ctypes.data if want_L else None))
         return alpha, L
 
-    def kernel_matrix(self, X, X2, kernel_id, variance, lengthscale, diag_add=0.0):
+    def kernel_matrix(self, X, X2, kernel_id, variance, lengthscale, diag_add=0.0, ARD=None):
         X = _f64(X)
-        ls = _f64(np.atleast_1d(lengthscale))
         N, d = X.shape
+        ls, ard = self._ard(lengthscale, d, ARD)
         if X2 is None:
             M = N
             out = np.empty((N, N), dtype=np.float64)
@@ -204,7 +265,7 @@ class Handle:
             out = np.empty((N, M), dtype=np.float64)
             x2p = X2.ctypes.data
         rc = self.lib.gpx_kernel_matrix(self._h, X.ctypes.data, N, d, x2p, M, int(kernel_id), float(variance),
-                                        ls.ctypes.data_as(_c_double_p), ls.size, float(diag_add), out.ctypes.data)
+                                        ls.ctypes.data_as(_c_double_p), ls.size, ard, float(diag_add), out.ctypes.data)
         self._check(rc)
         return out
 

@@ -17,8 +17,10 @@ with growing jitter like ``jitchol`` before raising ``LinAlgError``.
 
 ``do_optimize=True`` runs GPy's randomize + L-BFGS-B loop with the objective and its
 gradient evaluated on the GPU (``optimize.py``, ``gpx_lml_grad``); ``num_mcmc > 0`` runs GPy's HMC recipe on the same
-objective and predictions gain the leading hyper-sample axis.  Not built: GPy prior objects on the noise and the RBF
-Jacobian/Hessian helpers (``NotImplementedError`` instead of silently doing something else).
+objective and predictions gain the leading hyper-sample axis (one resident factorisation per retained sample).
+``add_observations`` appends to the resident factor (``gpx_append``) when only the data changed; ``get_mean`` and small
+batches take the latency path of ``gpx_predict``; ``predict_jacobian`` / ``predict_hessian`` evaluate the reference's
+expressions from sums computed on the GPU.  Not built: GPy prior objects on the noise (``NotImplementedError``).
 """
 import os
 import pathlib
@@ -165,6 +167,15 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         self.device = None
         self.randomize_before_optimize = True   # GPModel calls gpy_model.randomize() before optimize()
         self.max_iters = 1000                    # paramz default
+        # additive knobs (not in the reference)
+        self.distributed = None                  # shard the factor over the torch.distributed ranks: True / False, or None =
+                                                 # only when the environment says GPX_DISTRIBUTED=1 (opt-in: ranks of a sweep
+                                                 # that fit different models must not meet in a collective)
+        self.incremental = True                  # add_observations appends to the resident factor when it can
+        self.max_cached_thetas = 16              # HMC: factorisations kept resident, one handle per hyper-sample
+        self._normalize_input = False            # fused NormalizerModel (set by NormalizerModel, normalizer.py)
+        self._normalize_output = False
+        self._theta_handles = {}
 
     @classmethod
     def process_config(cls, *, kernel=None, **kwargs):
@@ -180,7 +191,14 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         state = self.__dict__.copy()
         state['_handle'] = None
         state['_fitted_theta'] = None
+        state['_theta_handles'] = {}
         return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        for k, v in (("distributed", None), ("incremental", True), ("max_cached_thetas", 16), ("_normalize_input", False),
+                     ("_normalize_output", False), ("_theta_handles", {})):
+            self.__dict__.setdefault(k, v)
 
     def get_common_hyperparameters(self):
         return {
@@ -207,28 +225,48 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         self.kernel.lengthscale = theta[i + 1:i + 1 + nl].copy()
         self.noise_variance = float(theta[i + 1 + nl])
 
+    # -- handles -------------------------------------------------------------------------------------------------
+    def _wants_sharding(self):
+        if self.distributed is not None:
+            return bool(self.distributed)
+        return os.environ.get("GPX_DISTRIBUTED", "0") == "1"
+
+    def _new_handle(self, shard):
+        h = _gpx.Handle(self.device if self.device is not None else _default_device())
+        if shard and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                raise _gpx.GpxError("a sharded GPModel needs an initialised torch.distributed process group (torchrun)")
+            if dist.get_world_size() > 1:
+                from . import distributed as gdist
+                gdist.init_handle_comm(h, dist)
+        h.set_normalizer(self._normalize_input, self._normalize_output)
+        return h
+
     def _get_handle(self):
         if self._handle is None:
-            self._handle = _gpx.Handle(self.device if self.device is not None else _default_device())
-            # one process per GPU: when torch.distributed is up (torchrun), shard the factor over the ranks
-            if os.environ.get("GPX_DISTRIBUTED", "1") != "0" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-                import torch.distributed as dist
-                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                    from . import distributed as gdist
-                    gdist.init_handle_comm(self._handle, dist)
+            # one process per GPU: sharding is OPT-IN (model.distributed = True or GPX_DISTRIBUTED=1); every rank must
+            # then call init / get_statistics with identical data and hyper-parameters (checked at fit time)
+            self._handle = self._new_handle(self._wants_sharding())
         return self._handle
 
-    def _factorize(self, retry=True):
-        """K-build + Cholesky + alpha + LML on the GPU for the current parameters (jitchol-style retry)."""
-        h = self._get_handle()
+    def _sharded(self, h=None):
+        h = h or self._handle
+        return h is not None and getattr(h, "world", 1) > 1
+
+    def _fit_handle(self, h, retry=True):
+        """K-build + Cholesky + alpha + LML on handle ``h`` for the current parameters (jitchol-style retry)."""
         X, Y = self._X, self._Y
+        if self._sharded(h):
+            from . import distributed as gdist
+            gdist.check_same_problem(h, X, Y, self._param_array())
         jitter = self.jitter
         extra = 0.0
         tries = 0
         while True:
             try:
                 h.fit(X, Y, self.kernel.kernel_id, float(self.kernel.variance[0]), self.kernel.lengthscale,
-                      self.noise_variance, jitter + extra, self.mean_const)
+                      self.noise_variance, jitter + extra, self.mean_const, ARD=self.kernel.ARD)
                 break
             except _gpx.NotPositiveDefiniteError:
                 if not retry:
@@ -240,6 +278,9 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                 diag_mean = float(self.kernel.variance[0]) + self.noise_variance + jitter
                 extra = diag_mean * 1e-6 * 10 ** (tries - 1)
                 warnings.warn("Added jitter of {:.10e}".format(extra))
+
+    def _factorize(self, retry=True):
+        self._fit_handle(self._get_handle(), retry=retry)
         self._fitted_theta = self._param_array().copy()
 
     def _ensure_fitted(self, theta):
@@ -247,6 +288,31 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
             self._set_params(theta)
             self._factorize()
 
+    def _handle_for_theta(self, theta):
+        """The fitted handle for hyper-sample ``theta``.  One sample: the model's own handle.  HMC (T > 1): the reference
+        re-factorises for every theta at every predict (``gpy_model[:] = theta``, core_models.py:249-251); here up to
+        ``max_cached_thetas`` factorisations stay resident, one handle each, so repeated predictions cost O(T N^2 N*)
+        instead of O(T N^3)."""
+        if len(self._current_thetas) == 1 or self._sharded() or self._wants_sharding():
+            self._ensure_fitted(theta)
+            return self._get_handle()
+        key = np.asarray(theta, dtype=np.float64).tobytes()
+        h = self._theta_handles.get(key)
+        if h is None:
+            while len(self._theta_handles) >= max(1, self.max_cached_thetas):
+                self._theta_handles.pop(next(iter(self._theta_handles))).close()
+            h = self._new_handle(False)
+            self._set_params(theta)
+            self._fit_handle(h)
+            self._theta_handles[key] = h
+        return h
+
+    def _drop_theta_handles(self):
+        for h in self._theta_handles.values():
+            h.close()
+        self._theta_handles = {}
+
+    # -- fitting -------------------------------------------------------------------------------------------------
     def _fit(self, X, Y, Y_dir=None):
         assert X.shape[0] == Y.shape[0], \
             "X and Y has to match size. It was {} and {} respectively".format(X.shape[0], Y.shape[0])
@@ -255,13 +321,18 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         first_fit = self.noise_variance is None
         if first_fit or self.kernel is None:
             self.kernel = self.kernel_constructor(input_dim)
-
-        if self.mean_prior is not None:
-            self.mean_const = float(np.mean(Y))
-        else:
-            self.mean_const = 0.0
+        self._drop_theta_handles()
 
         if first_fit:
+            # The reference builds gpy_model once (core_models.py:190-207) and later only calls set_XY (:209): the Constant
+            # mean mapping keeps the value it was created with (or the optimised one), it is NOT reset to the new mean(Y).
+            if self.mean_prior is not None:
+                Yn = Y
+                if self._normalize_output:       # the inner model of a NormalizerModel sees z-scored outputs
+                    Yn = (Y - np.mean(Y, axis=0)) / np.std(Y, axis=0)
+                self.mean_const = float(np.mean(Yn))
+            else:
+                self.mean_const = 0.0
             self.noise_variance = 1.0  # GPy GPRegression default likelihood variance
             self._noise_fixed = False
             if self.noise_prior:
@@ -272,6 +343,9 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                 else:
                     raise NotImplementedError("GPy prior objects on the noise variance are not supported; "
                                               "pass a number (fixed noise) or None (free noise)")
+        if self.do_optimize and self._wants_sharding() and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            raise _gpx.GpxError("do_optimize / num_mcmc need gpx_lml_grad, which is not available on a sharded handle: "
+                                "optimise on one GPU (model.distributed = False), then refit sharded with do_optimize=False")
         if self.do_optimize and self.num_mcmc > 0:
             self._sample_hyperparameters()           # sets _current_thetas (one per retained HMC sample)
             return
@@ -280,6 +354,32 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         else:
             self._factorize()
         self._current_thetas = [self._param_array()]
+
+    def add_observations(self, X_new, Y_new, Y_dir_new=None):
+        """Reference ``BaseModel.add_observations`` (core_models.py:65-77) concatenates and refits from scratch, once
+        per Bayesian-optimisation step (src/algorithms.py:120-143).  With fixed hyper-parameters the refit is replaced
+        by ``gpx_append``: the new rows of K are solved against the resident factor (O(k N^2)); anything that changes
+        more than the data (do_optimize, HMC, the normaliser's statistics, a sharded factor) takes the reference's route."""
+        assert self._X is not None, "Call init first"
+        can_append = (self.incremental and not self.do_optimize and self._handle is not None
+                      and self._current_thetas is not None and len(self._current_thetas) == 1
+                      and self._fitted_theta is not None and np.array_equal(self._fitted_theta, self._current_thetas[0])
+                      and not self._sharded() and not (self._normalize_input or self._normalize_output)
+                      and self.Y_dir is None)
+        if not can_append:
+            return super().add_observations(X_new, Y_new, Y_dir_new)
+        X_new = np.asarray(X_new, dtype=np.float64)
+        Y_new = np.asarray(Y_new, dtype=np.float64)
+        assert X_new.shape[0] == Y_new.shape[0] and X_new.shape[1:] == self._X.shape[1:] and Y_new.shape[1:] == self._Y.shape[1:]
+        h = self._handle
+        h.set_option("reserve_rows", max(256, self._X.shape[0] // 8))   # later (re)layouts leave room for the next appends
+        try:
+            h.append(X_new, Y_new)
+        except (_gpx.NotPositiveDefiniteError, _gpx.AppendUnsupported):
+            self._fitted_theta = None
+            return super().add_observations(X_new, Y_new, Y_dir_new)
+        self._X = np.concatenate([self._X, X_new])
+        self._Y = np.concatenate([self._Y, Y_new])
 
     def _free_parameter_plumbing(self):
         """(names, positive mask, unpack(theta), objective(theta) -> (lml, grad), theta0) for the free parameters in GPy's
@@ -300,7 +400,7 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
 
         def objective(theta):
             unpack(theta)
-            self._factorize(retry=False)
+            self._factorize(retry=True)   # GPy's inference runs jitchol inside every objective evaluation
             h = self._get_handle()
             g = h.lml_grad(nl)            # [variance, ls..., noise, mean]
             out = ([g[nl + 2]] if has_mean else []) + [g[0]] + list(g[1:1 + nl]) + ([] if self._noise_fixed else [g[nl + 1]])
@@ -337,24 +437,29 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         self._factorize()
         self.optimization_info = info
 
-    def _predict(self, X, full_cov=True):
+    # -- prediction ----------------------------------------------------------------------------------------------
+    def _predict(self, X, full_cov=True, want_var=True):
         num_X = X.shape[0]
         num_obj = self.output_dim
         T = len(self._current_thetas)
         mean = np.zeros((T, num_X, num_obj))
         covar = np.zeros((T, num_X, num_X, num_obj)) if full_cov else None
-        var = None if full_cov else np.zeros((T, num_X, num_obj))
+        var = None if (full_cov or not want_var) else np.zeros((T, num_X, num_obj))
+        fused_y = bool(self._normalize_output)
         for i, theta in enumerate(self._current_thetas):
-            self._ensure_fitted(theta)
-            h = self._get_handle()
+            h = self._handle_for_theta(theta)
             if full_cov:
                 mean_i, cov_i = h.predict_cov(X, include_noise=True, output_dim=num_obj)
                 mean[i, :] = mean_i
                 covar[i, :] = cov_i[:, :, None]
+            elif not want_var:
+                mean[i, :] = h.predict(X, want_var=False, output_dim=num_obj)[0]
             else:
-                mean_i, var_i = h.predict(X, want_var=True, include_noise=True, output_dim=num_obj)
+                # with the fused output normaliser every output carries its own variance scale (var_cols = O)
+                mean_i, var_i = h.predict(X, want_var=True, include_noise=True, output_dim=num_obj,
+                                          var_cols=num_obj if (fused_y and num_obj > 1) else 1)
                 mean[i, :] = mean_i
-                var[i, :] = var_i[:, None]
+                var[i, :] = var_i if var_i.ndim == 2 else var_i[:, None]
         if full_cov:
             return mean, covar
         return mean, var
@@ -363,6 +468,13 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         assert self._current_thetas is not None, "Call init first"
         return self._predict(np.asarray(X), full_cov=full_cov)
 
+    def get_mean(self, X):
+        """Reference: ``get_statistics(X, full_cov=False)[0]`` (core_models.py:93-94), i.e. GPy computes the variance too
+        and throws it away.  Here the variance pass is skipped: a 1-row call (src/growth_model_GPR/ipopt_wrapper.py:55
+        issues them by the million) is three kernels replayed as one CUDA graph."""
+        assert self._current_thetas is not None, "Call init first"
+        return self._predict(np.asarray(X), full_cov=False, want_var=False)[0]
+
     def get_marginal_log_likelihood(self, X=None, Y=None):
         """Un-normalised log marginal likelihood of the fitted data (GPy ``log_likelihood()``)."""
         if X is not None and Y is not None and (X is not self._X or Y is not self._Y):
@@ -370,15 +482,56 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         self._ensure_fitted(self._current_thetas[0])
         return self._get_handle().lml()[0]
 
-    def predict_jacobian(self, X, full_cov=True):
-        """Reference core_models.py:313-333.  There the method reads ``self.normalizer``, an attribute GPModel never
-        defines, so it cannot run as written; not built here."""
-        raise NotImplementedError("predict_jacobian is not built (the reference version depends on an undefined "
-                                  "`self.normalizer`); see SURVEY.md section 8(f)")
+    # -- posterior-mean derivatives (reference core_models.py:313-380; consumer: CurvatureAcquisition,
+    #    src/acquisition_functions.py:86,113) --------------------------------------------------------------------------
+    def _raw_moments(self, X, order):
+        """S0 (N*), S1 (N*, D), S2 (N*, D, D): sums over the training points of w, w dx_k, w dx_k dx_l with
+        w = k(x_j, x*) alpha_j and dx = x* - x_j in INPUT coordinates (the device works in the kernel's coordinates: the
+        ARD scaling is undone here)."""
+        from .kernels import GPyRBF
+        assert isinstance(self.kernel, GPyRBF), "Only support RBF for now"     # reference core_models.py:343
+        assert not (self._normalize_input or self._normalize_output), \
+            "derivatives are taken in the coordinates the GP sees; call them on the un-wrapped GPModel"
+        self._ensure_fitted(self._current_thetas[0])
+        X = np.asarray(X, dtype=np.float64)
+        S0, S1, S2 = self._get_handle().predict_moments(X, order=order)
+        if self.kernel.ARD:
+            ls = self.kernel.lengthscale
+            S1 = S1 * ls[None, :]
+            if S2 is not None:
+                S2 = S2 * ls[None, :, None] * ls[None, None, :]
+        return S0, S1, S2
 
-    def predict_hessian(self, X, full_cov=True):
-        """Reference core_models.py:335-380 (RBF only, same undefined ``self.normalizer``); not built here."""
-        raise NotImplementedError("predict_hessian is not built; see SURVEY.md section 8(f)")
+    def _lengthscale_per_dim(self):
+        D = self._X.shape[1]
+        ls = self.kernel.lengthscale
+        return ls if ls.size == D else np.repeat(ls, D)
+
+    def predict_jacobian(self, X, full_cov=True, exact=False):
+        """Jacobian of the posterior mean, shape (N*, D), and None for its variance (reference core_models.py:313-333).
+
+        The reference's expression is ``-Lambda^-1 sum_j (x* - x_j) k(x_j, x*) alpha_j`` with ``Lambda^-1 = diag(1 / l)``
+        -- one power of the lengthscale short of the derivative of an RBF mean -- and its first line reads an attribute
+        (``self.normalizer``) GPModel never defines.  Default: the reference's expression, evaluated on the GPU
+        (``gpx_predict_moments``); ``exact=True``: the true gradient ``-S1 / l^2``."""
+        _, S1, _ = self._raw_moments(X, order=1)
+        l = self._lengthscale_per_dim()
+        return (-S1 / (l ** 2 if exact else l)[None, :]), None
+
+    def predict_hessian(self, X, full_cov=True, exact=False):
+        """Hessian of the posterior mean, (N*, D, D), and None (reference core_models.py:335-380; RBF only).
+
+        Reference-literal by default: ``H[i,k,l] = -(1/l_k) (S0[i] - S2[i,k,l] / l_l)`` -- the reference adds ``S0`` to
+        every entry (its ``Ones`` einsum) and, like the Jacobian, uses 1/l where the calculus gives 1/l^2.
+        ``exact=True``: ``S2[i,k,l] / (l_k^2 l_l^2) - delta_kl S0[i] / l_k^2``."""
+        S0, _, S2 = self._raw_moments(X, order=2)
+        l = self._lengthscale_per_dim()
+        if exact:
+            H = S2 / (l[None, :, None] ** 2 * l[None, None, :] ** 2)
+            idx = np.arange(l.size)
+            H[:, idx, idx] -= S0[:, None] / l[None, :] ** 2
+            return H, None
+        return -(S0[:, None, None] - S2 / l[None, None, :]) / l[None, :, None], None
 
     def phase_times_ms(self):
         """Per-phase CUDA-event times of the last fit / predict (the numbers Runner logs as time.training/pred)."""

@@ -18,65 +18,7 @@
 // Backward substitution: row-oriented, z_J lives with the owner of column J; one 4 KB broadcast of alpha per panel.
 // Predict: test tiles are sharded over ranks; the panels of L are re-broadcast (double buffered) while each rank runs
 // its K*-build + blocked triangular solve + row sum-of-squares; results are combined with one small all-reduce.
-#include <dlfcn.h>
-#include <nccl.h>
-
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/gpx.h"
-#include "gpx_common.cuh"
-
-// launchers from the other translation units
-void gpx_kbuild_init();
-int gpx_kbuild_max_d();
-int gpx_grad_max_d();
-void gpx_launch_kbuild_lower(TileMat L, int nt, int jfirst, int jstep, int ncols, const double* Xs, const double* xsq,
-                             int64_t N, int d, int kernel_id, double variance, double diag_add, cudaStream_t st);
-void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, double mean_const, double* mean,
-                            int64_t row0, int64_t Ns, cudaStream_t st);
-void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, double prior_var, double* var, int64_t row0, int64_t Ns,
-                           cudaStream_t st);
-void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double* out, cudaStream_t st);
-void gpx_launch_fwd_step(TileMat L, const double* linv, int nt, int J, double* b, double* z, int64_t Np, int O,
-                         int max_ctas, cudaStream_t st);
-void gpx_launch_bwd_step(TileMat L, const double* linv, int I, double* z, double* a, int64_t Np, int O,
-                         int compute_alpha, int ncols, int jbase, int jW, int jstride, int max_ctas, cudaStream_t st);
-void gpx_launch_lml(const double* linv, const double* alpha, const double* resid, int64_t Np, int O, double* out2,
-                    cudaStream_t st);
-void gpx_launch_resid(const double* Y, int64_t N, int64_t Np, int O, double mean_const, double* resid, cudaStream_t st);
-void gpx_launch_untranspose(const double* in, int64_t N, int64_t Np, int O, double* out, cudaStream_t st);
-void gpx_launch_identity_tiles(TileMat T, int nt, cudaStream_t st);
-void gpx_launch_lml_grad(TileMat Kinv, int nt, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
-                         double variance, const double* ls, int n_ls, const double* alpha, int O, int64_t Np,
-                         double* partial, double* out, cudaStream_t st);
-
-namespace {
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-};
-
-// NCCL is resolved at run time (dlopen) so that the library also loads where no libnccl is installed; the
-// single-GPU path never touches it.
-struct NcclApi {
-    void* lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;  // optional (NCCL >= 2.18)
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-    bool tried = false, ok = false;
-};
+#include "gpx_internal.cuh"
 
 NcclApi& nccl() {
     static NcclApi api;
@@ -104,145 +46,6 @@ NcclApi& nccl() {
     return api;
 }
 
-}  // namespace
-
-struct gpx_handle {
-    int device = 0;
-    int num_sms = 148;
-    cudaStream_t st = nullptr;    // main / update stream (U)
-    cudaStream_t st_f = nullptr;  // panel factorisation (F), high priority
-    cudaStream_t st_c = nullptr;  // communication (C), high priority
-    std::string err;
-    int64_t launches = 0;
-    int64_t bytes_alloc = 0;
-
-    // distribution
-    int rank = 0, world = 1;
-    ncclComm_t comm = nullptr;     // default configuration: bandwidth-bound transfers (predict re-broadcast, all-reduce)
-    ncclComm_t comm_lo = nullptr;  // at most 4 CTAs: the panel broadcasts that overlap the trailing updates
-    int nccl_lo_ctas = 4;
-
-    // options
-    int outer_tiles = 0;          // 0 = auto: 4 when sharded, else min(16, max(4, nt / 24)) (K of the trailing update)
-    int predict_batch_tiles = 0;  // 0 = auto
-    int sync_phases = 1;
-    int gemm_timing = 0;
-    int lookahead = 1;
-    int gemm_max_chunk = 0;               // 0 = auto: 16 on one GPU, 4 when sharded (shorter CTAs let the panel
-                                          // factorisation and NCCL kernels of the other streams in sooner)
-    int trace = 0;                        // 1: per-panel timeline events during the Cholesky (gpx_trace)
-    std::vector<cudaEvent_t> tev;         // 6 per panel + 1 base, timing enabled
-    std::vector<float> trace_ms;          // 6 per panel: factor start, factor end, panel ready, (a) end, fwd end, (b) end
-    std::vector<cudaEvent_t> gemm_ev;  // pairs, grown on demand
-    size_t gemm_ev_used = 0;
-    double gemm_ms = 0, gemm_flops = 0;
-    int64_t gemm_launches = 0;
-
-    // problem
-    bool fitted = false;
-    int64_t N = 0, Np = 0;
-    int nt = 0, d = 0, O = 0, kernel_id = 0, n_ls = 0;
-    int W = 4, npanels = 0;  // W = outer_tiles frozen at fit time
-    double variance = 1, noise = 1, jitter = 1e-8, mean_const = 0;
-    double lml = 0, logdet = 0, quad = 0;
-
-    DevBuf Xs, xsq, ls, L, linv, coloff, vcoloff, linv_coloff, resid, work1, work2, alpha, scal, info;
-    DevBuf stage;
-    DevBuf gbuf[2];                     // group buffers (world > 1): the M panels of a group, contiguous; double buffered
-    int group_panels = 1;               // M: panels per delayed far update when sharded (measured: no gain from M = 4,
-                                        // 2587 vs 2591 ms at 4 GPUs / N = 100k, so the simpler M = 1 is the default)
-    DevBuf cache;                       // received panels kept resident after the fit (world > 1) so that predict does not
-    DevBuf ucoloff;                     // have to re-broadcast them; ucoloff = column offsets of own + cached columns
-    std::vector<int64_t> h_ucoloff;     // relative to the base of L (pointer arithmetic across the two allocations)
-    int cache_panels = 0;               // panels [0, cache_panels) are resident on every rank
-    int64_t cache_limit_mb = -1;        // option "cache_mb": -1 auto (free memory minus a reserve), 0 disables
-    std::vector<int64_t> h_coloff;      // local offsets (-1: not owned)
-    std::vector<int64_t> h_vcoloff;     // virtual full packed offsets
-    std::vector<cudaEvent_t> pev;       // per-panel events (3 per panel), no timing
-
-    // predict workspaces
-    DevBuf Tt, tt_coloff, Xt, xtsq, mean_partial, dmean, dvar;
-
-    cudaEvent_t ev[2 * GPX_NUM_PHASES];
-    float phase_ms[GPX_NUM_PHASES];
-};
-
-namespace {
-
-int fail(gpx_t* h, int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (h) h->err = buf;
-    return code;
-}
-
-#define GPX_CUDA(h, call)                                                                                \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(h, -2, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
-    } while (0)
-
-#define GPX_NCCL(h, call)                                                                                \
-    do {                                                                                                 \
-        ncclResult_t r_ = (call);                                                                        \
-        if (r_ != ncclSuccess)                                                                           \
-            return fail(h, -7, "NCCL error %s at %s:%d (%s)", nccl().GetErrorString(r_), __FILE__, __LINE__, #call); \
-    } while (0)
-
-int ensure(gpx_t* h, DevBuf& b, size_t bytes) {
-    if (b.bytes >= bytes && b.p) return 0;
-    if (b.p) {
-        cudaFree(b.p);
-        h->bytes_alloc -= (int64_t)b.bytes;
-        b.p = nullptr;
-        b.bytes = 0;
-    }
-    if (bytes == 0) return 0;
-    cudaError_t e = cudaMalloc(&b.p, bytes);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return fail(h, -3, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-    }
-    b.bytes = bytes;
-    h->bytes_alloc += (int64_t)bytes;
-    return 0;
-}
-
-void release(gpx_t* h, DevBuf& b) {
-    if (b.p) {
-        cudaFree(b.p);
-        h->bytes_alloc -= (int64_t)b.bytes;
-    }
-    b.p = nullptr;
-    b.bytes = 0;
-}
-
-template <typename T>
-T* ptr(const DevBuf& b) { return reinterpret_cast<T*>(b.p); }
-
-void phase_begin(gpx_t* h, int ph) { if (h->sync_phases) cudaEventRecord(h->ev[2 * ph], h->st); }
-void phase_end(gpx_t* h, int ph) { if (h->sync_phases) cudaEventRecord(h->ev[2 * ph + 1], h->st); }
-void phase_collect(gpx_t* h, int ph) {
-    if (!h->sync_phases) return;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev[2 * ph], h->ev[2 * ph + 1]) == cudaSuccess) h->phase_ms[ph] = ms;
-    else cudaGetLastError();
-}
-
-// stage a caller buffer onto the device (host pointer -> device copy on the main stream, or passthrough)
-int to_device(gpx_t* h, const double* src, size_t count, int mem, DevBuf& staging, const double** out) {
-    if (mem == GPX_MEM_DEVICE) { *out = src; return 0; }
-    size_t bytes = count * sizeof(double);
-    int rc = ensure(h, staging, bytes);
-    if (rc) return rc;
-    GPX_CUDA(h, cudaMemcpyAsync(staging.p, src, bytes, cudaMemcpyHostToDevice, h->st));
-    *out = ptr<double>(staging);
-    return 0;
-}
 
 // every DMMA tile-GEMM launch goes through here (optionally bracketed by events for the roofline numbers)
 void gemm(gpx_t* h, const GemmJob& job_in, cudaStream_t st) {
@@ -280,75 +83,6 @@ void gemm_collect(gpx_t* h) {
     h->gemm_ev_used = 0;
 }
 
-// ---- distribution helpers ---------------------------------------------------------------------------------------
-inline int panel_begin(const gpx_t* h, int p) { return p * h->W; }
-inline int panel_end(const gpx_t* h, int p) { int e = (p + 1) * h->W; return e < h->nt ? e : h->nt; }
-inline int panel_owner(const gpx_t* h, int p) { return p % h->world; }
-inline bool owns_panel(const gpx_t* h, int p) { return panel_owner(h, p) == h->rank; }
-inline int64_t panel_elems(const gpx_t* h, int p) {
-    int64_t e = 0;
-    for (int c = panel_begin(h, p); c < panel_end(h, p); c++) e += (int64_t)(h->nt - c) * GPX_TILE_ELEMS;
-    return e;
-}
-// first panel >= q owned by this rank (may be >= npanels)
-inline int next_owned_panel(const gpx_t* h, int q) {
-    int r = q % h->world;
-    int add = (h->rank - r + h->world) % h->world;
-    return q + add;
-}
-// number of tile columns in owned panels q, q+world, q+2 world, ... (q must be owned)
-inline int owned_cols_from(const gpx_t* h, int q) {
-    int n = 0;
-    for (int p = q; p < h->npanels; p += h->world) n += panel_end(h, p) - panel_begin(h, p);
-    return n;
-}
-
-// receive buffers alternate over the panels this rank does NOT own
-inline int recv_index(const gpx_t* h, int p) {
-    int owned_before = (p > h->rank) ? (p - h->rank + h->world - 1) / h->world : 0;
-    return p - owned_before;
-}
-inline double* recv_buf(gpx_t* h, int p) { return reinterpret_cast<double*>(h->gbuf[recv_index(h, p) & 1].p); }  // predict sweep
-// the previous non-owned panel that used the same receive buffer as panel p (-1: none)
-inline int prev_same_buffer_panel(const gpx_t* h, int p) {
-    int seen = 0;
-    for (int q = p - 1; q >= 0; q--) {
-        if (!owns_panel(h, q) && ++seen == 2) return q;
-    }
-    return -1;
-}
-
-TileMat lmat(gpx_t* h) { return TileMat{ptr<double>(h->L), ptr<int64_t>(h->coloff), 1}; }
-TileMat linvmat(gpx_t* h) { return TileMat{ptr<double>(h->linv), ptr<int64_t>(h->linv_coloff), 1}; }
-// own + cached columns through one table (offsets relative to L's base)
-TileMat umat(gpx_t* h) { return TileMat{ptr<double>(h->L), ptr<int64_t>(h->ucoloff), 1}; }
-inline bool panel_cached(const gpx_t* h, int p) { return h->world > 1 && p < h->cache_panels && !owns_panel(h, p); }
-// where a non-owned panel is received: its resident cache slot, or one of the two rotating buffers
-inline double* panel_recv_ptr(gpx_t* h, int p) {
-    if (panel_cached(h, p)) return ptr<double>(h->L) + h->h_ucoloff[panel_begin(h, p)];
-    return recv_buf(h, p);
-}
-// the factored panel p as an operand: the local storage on its owner, the cache or a receive buffer elsewhere
-TileMat panel_mat(gpx_t* h, int p) {
-    if (owns_panel(h, p)) return lmat(h);
-    if (panel_cached(h, p)) return umat(h);
-    return TileMat{recv_buf(h, p) - h->h_vcoloff[panel_begin(h, p)], ptr<int64_t>(h->vcoloff), 1};
-}
-
-// per-panel events: 0 panel ready (factored / received), 3 factored on stream F; per group (stored at its first panel):
-// 1 far update of the next group's panels done, 2 far update done (group buffer free).  The predict sweep re-uses 0 / 2.
-cudaEvent_t pevent(gpx_t* h, int p, int which) { return h->pev[(size_t)4 * p + which]; }
-
-int ensure_panel_events(gpx_t* h, int npanels) {
-    size_t need = (size_t)4 * npanels;
-    while (h->pev.size() < need) {
-        cudaEvent_t e;
-        GPX_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        h->pev.push_back(e);
-    }
-    return 0;
-}
-
 // broadcast panel p (its packed columns and, optionally, its inverted diagonal tiles) from its owner, on stream C.
 // During the factorisation (with_linv) the low-CTA communicator is used: an NCCL channel pins an SM for the whole
 // transfer and the tile GEMM needs a whole SM's shared memory, so NCCL's default ~24 channels cost the overlapped
@@ -377,31 +111,34 @@ void trace_rec(gpx_t* h, int p, int which, cudaStream_t st) {
     cudaEventRecord(h->tev[1 + (size_t)6 * p + which], st);
 }
 
-// factor panel p in place on its owner (stream F)
-void factor_panel(gpx_t* h, int p) {
-    const int nt = h->nt, p0 = panel_begin(h, p), p1 = panel_end(h, p);
+// factor the tile columns [c0, c1) in place (rows up to nt) on stream st: POTRF + inverse of the diagonal tile, TRSM of
+// the column as a DMMA GEMM against the inverted tile, rank-128 update of the remaining columns of the range
+void factor_cols(gpx_t* h, int c0, int c1, int nt, cudaStream_t st) {
     TileMat L = lmat(h), Li = linvmat(h);
     int* info = ptr<int>(h->info);
-    for (int k = p0; k < p1; k++) {
+    for (int k = c0; k < c1; k++) {
         double* diag = ptr<double>(h->L) + h->h_coloff[k];
-        gpx_launch_potrf_tile(diag, ptr<double>(h->linv) + (int64_t)k * GPX_TILE_ELEMS, info, k, h->st_f);
+        gpx_launch_potrf_tile(diag, ptr<double>(h->linv) + (int64_t)k * GPX_TILE_ELEMS, info, k, st);
         h->launches++;
         if (k + 1 < nt) {
             GemmJob t{};  // TRSM: L(I,k) <- L(I,k) * Linv_k^T for I > k
             t.A = L; t.B = Li; t.C = L;
             t.tri = 0; t.i0 = k + 1; t.i1 = nt; t.ncols = 1; t.jbase = k; t.jW = GPX_JW_CONTIG; t.jstride = 0;
             t.k0 = k; t.k1 = k + 1; t.bdiag = 1; t.overwrite = 1;
-            gemm(h, t, h->st_f);
+            gemm(h, t, st);
         }
-        if (k + 1 < p1) {
-            GemmJob u{};  // update the remaining columns of this panel with column k
+        if (k + 1 < c1) {
+            GemmJob u{};  // update the remaining columns of this range with column k
             u.A = L; u.B = L; u.C = L;
-            u.tri = 1; u.i0 = k + 1; u.i1 = nt; u.ncols = p1 - (k + 1); u.jbase = k + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+            u.tri = 1; u.i0 = k + 1; u.i1 = nt; u.ncols = c1 - (k + 1); u.jbase = k + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
             u.k0 = k; u.k1 = k + 1; u.bdiag = 0; u.overwrite = 0;
-            gemm(h, u, h->st_f);
+            gemm(h, u, st);
         }
     }
 }
+
+// factor panel p in place on its owner (stream F)
+void factor_panel(gpx_t* h, int p) { factor_cols(h, panel_begin(h, p), panel_end(h, p), h->nt, h->st_f); }
 
 // Blocked right-looking Cholesky with look-ahead, grouped ("delayed") far updates and fused forward substitution.
 // b (work1) is consumed, z -> work2.
@@ -580,11 +317,11 @@ int backward_solve(gpx_t* h) {
     return 0;
 }
 
-}  // namespace
+
 
 extern "C" {
 
-int gpx_version(void) { return 101; }
+int gpx_version(void) { return 200; }
 
 int gpx_create(gpx_t** out, int device) {
     if (!out) return -1;
@@ -627,8 +364,11 @@ void gpx_destroy(gpx_t* h) {
     DevBuf* all[] = {&h->Xs, &h->xsq, &h->ls, &h->L, &h->linv, &h->coloff, &h->vcoloff, &h->linv_coloff, &h->resid,
                      &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->gbuf[0], &h->gbuf[1], &h->cache,
                      &h->ucoloff, &h->Tt,
-                     &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar};
+                     &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar, &h->sp, &h->xstats, &h->ystats};
     for (DevBuf* b : all) release(h, *b);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->ev_caller) cudaEventDestroy(h->ev_caller);
     for (auto& e : h->ev) cudaEventDestroy(e);
     for (auto& e : h->gemm_ev) cudaEventDestroy(e);
     for (auto& e : h->pev) cudaEventDestroy(e);
@@ -690,6 +430,8 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "nccl_lo_ctas")) { h->nccl_lo_ctas = (int)value; return 0; }  // takes effect at gpx_comm_init
     if (!strcmp(name, "trace")) { h->trace = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_max_chunk")) { h->gemm_max_chunk = (int)value; return 0; }
+    if (!strcmp(name, "reserve_rows")) { if (value < 0) return fail(h, -1, "bad reserve_rows"); h->reserve_rows = value; return 0; }
+    if (!strcmp(name, "predict_graph")) { h->predict_graph = value ? 1 : 0; h->gen++; return 0; }
     return fail(h, -1, "unknown option %s", name);
 }
 
@@ -720,21 +462,34 @@ int64_t gpx_trace(const gpx_t* h, double* out, int64_t capacity) {
 }
 
 int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O, int kernel_id, double variance,
-            const double* lengthscale, int n_ls, double noise, double jitter, double mean_const, int mem) {
+            const double* lengthscale, int n_ls, int ard, double noise, double jitter, double mean_const, int mem) {
     if (!h) return -1;
     if (!X || !Y || !lengthscale) return fail(h, -1, "null argument");
     if (N < 1 || d < 1 || O < 1) return fail(h, -1, "bad shape N=%lld d=%d O=%d", (long long)N, d, O);
     if (d > gpx_kbuild_max_d()) return fail(h, -1, "input dimension %d exceeds the supported maximum %d", d, gpx_kbuild_max_d());
     if (kernel_id < 0 || kernel_id > 3) return fail(h, -1, "unknown kernel id %d", kernel_id);
-    if (n_ls != 1 && n_ls != d) return fail(h, -1, "lengthscale must have 1 or d entries");
+    if (ard ? (n_ls != d) : (n_ls != 1))
+        return fail(h, -1, "lengthscale must have d entries with ARD and 1 entry without (got %d, d=%d, ARD=%d)", n_ls, d, ard);
     if (!(variance > 0) || !(noise + jitter > 0)) return fail(h, -1, "variance and noise+jitter must be positive");
     for (int i = 0; i < n_ls; i++) if (!(lengthscale[i] > 0)) return fail(h, -1, "lengthscale must be positive");
     GPX_CUDA(h, cudaSetDevice(h->device));
     h->fitted = false;
+    { int rcw = wait_for_caller(h); if (rcw) return rcw; }
     const int nt = (int)((N + GPX_TILE - 1) / GPX_TILE);
-    const int64_t Np = (int64_t)nt * GPX_TILE;
+    // Capacity for gpx_append (single-GPU handles): the column-packed factor and the [o][Np] vectors are laid out for
+    // cap_nt >= nt tile rows, so that rows can be appended in place until the reserve is used up (then gpx_append
+    // re-lays the storage out).  Np is the padded vector length / stride; rows >= N hold zeros (identity in L).
+    int cap_nt = nt;
+    if (h->world == 1 && h->reserve_rows > 0) cap_nt = (int)((N + h->reserve_rows + GPX_TILE - 1) / GPX_TILE);
+    const int64_t Np = (int64_t)cap_nt * GPX_TILE;
+    h->cap_nt = cap_nt;
+    h->gen++;   // invalidates captured predict graphs
     h->N = N; h->Np = Np; h->nt = nt; h->d = d; h->O = O; h->kernel_id = kernel_id; h->n_ls = n_ls;
     h->variance = variance; h->noise = noise; h->jitter = jitter; h->mean_const = mean_const;
+    h->ard = ard ? 1 : 0;
+    h->rdiv = ard ? 1.0 : lengthscale[0];
+    h->h_ls.assign(lengthscale, lengthscale + n_ls);
+    h->fit_norm_x = h->norm_x; h->fit_norm_y = h->norm_y;
     if (h->outer_tiles > 0) h->W = h->outer_tiles;
     else if (h->world > 1) h->W = 4;
     else { h->W = nt / 24; if (h->W < 4) h->W = 4; if (h->W > 16) h->W = 16; }
@@ -743,23 +498,22 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     for (auto& m : h->phase_ms) m = 0.f;
 
     // packed lower-triangular tile storage: only the columns of the panels this rank owns
-    h->h_coloff.assign(nt, -1);
+    h->h_coloff.assign(cap_nt, -1);
     h->h_vcoloff.resize(nt);
-    std::vector<int64_t> lc(nt);
+    std::vector<int64_t> lc(cap_nt);
     int64_t off = 0, voff = 0, max_panel = 0;
-    for (int c = 0; c < nt; c++) {
-        h->h_vcoloff[c] = voff;
-        voff += (int64_t)(nt - c) * GPX_TILE_ELEMS;
+    for (int c = 0; c < cap_nt; c++) {
+        if (c < nt) { h->h_vcoloff[c] = voff; voff += (int64_t)(nt - c) * GPX_TILE_ELEMS; }
         lc[c] = (int64_t)c * GPX_TILE_ELEMS;
-        if (panel_owner(h, c / h->W) == h->rank) { h->h_coloff[c] = off; off += (int64_t)(nt - c) * GPX_TILE_ELEMS; }
+        if (panel_owner(h, c / h->W) == h->rank) { h->h_coloff[c] = off; off += (int64_t)(cap_nt - c) * GPX_TILE_ELEMS; }
     }
     for (int p = 0; p < h->npanels; p++) { int64_t e = panel_elems(h, p); if (e > max_panel) max_panel = e; }
     int rc;
     if ((rc = ensure(h, h->L, (size_t)(off > 0 ? off : 1) * 8))) return rc;
-    if ((rc = ensure(h, h->linv, (size_t)nt * GPX_TILE_BYTES))) return rc;
-    if ((rc = ensure(h, h->coloff, (size_t)nt * 8))) return rc;
+    if ((rc = ensure(h, h->linv, (size_t)cap_nt * GPX_TILE_BYTES))) return rc;
+    if ((rc = ensure(h, h->coloff, (size_t)cap_nt * 8))) return rc;
     if ((rc = ensure(h, h->vcoloff, (size_t)nt * 8))) return rc;
-    if ((rc = ensure(h, h->linv_coloff, (size_t)nt * 8))) return rc;
+    if ((rc = ensure(h, h->linv_coloff, (size_t)cap_nt * 8))) return rc;
     if ((rc = ensure(h, h->Xs, (size_t)Np * d * 8))) return rc;
     if ((rc = ensure(h, h->xsq, (size_t)Np * 8))) return rc;
     if ((rc = ensure(h, h->ls, (size_t)n_ls * 8))) return rc;
@@ -822,9 +576,9 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
         }
         GPX_CUDA(h, cudaMemcpyAsync(h->ucoloff.p, h->h_ucoloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
     }
-    GPX_CUDA(h, cudaMemcpyAsync(h->coloff.p, h->h_coloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
+    GPX_CUDA(h, cudaMemcpyAsync(h->coloff.p, h->h_coloff.data(), (size_t)cap_nt * 8, cudaMemcpyHostToDevice, h->st));
     GPX_CUDA(h, cudaMemcpyAsync(h->vcoloff.p, h->h_vcoloff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
-    GPX_CUDA(h, cudaMemcpyAsync(h->linv_coloff.p, lc.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
+    GPX_CUDA(h, cudaMemcpyAsync(h->linv_coloff.p, lc.data(), (size_t)cap_nt * 8, cudaMemcpyHostToDevice, h->st));
     GPX_CUDA(h, cudaMemcpyAsync(h->ls.p, lengthscale, (size_t)n_ls * 8, cudaMemcpyHostToDevice, h->st));
     GPX_CUDA(h, cudaMemsetAsync(h->info.p, 0, 64, h->st));
     GPX_CUDA(h, cudaStreamSynchronize(h->st));  // lc / lengthscale are host temporaries
@@ -839,21 +593,36 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
 
     // K-build: only the owned panels' columns
     phase_begin(h, GPX_PHASE_KBUILD);
-    gpx_launch_scale_x(dX, N, Np, d, ptr<double>(h->ls), n_ls, ptr<double>(h->Xs), ptr<double>(h->xsq), h->st);
-    gpx_launch_resid(dY, N, Np, O, mean_const, ptr<double>(h->resid), h->st);
-    h->launches += 2;
+    // fused NormalizerModel: column means / population stds of the raw X and Y, computed here and applied by the loaders
+    if (h->fit_norm_x) {
+        if ((rc = ensure(h, h->xstats, (size_t)2 * d * 8))) { release(h, stageY); return rc; }
+        gpx_launch_col_stats(dX, N, d, ptr<double>(h->xstats), h->st);
+        h->launches++;
+    }
+    if (h->fit_norm_y) {
+        if ((rc = ensure(h, h->ystats, (size_t)2 * O * 8))) { release(h, stageY); return rc; }
+        gpx_launch_col_stats(dY, N, O, ptr<double>(h->ystats), h->st);
+        h->launches++;
+    }
+    prep_inputs(h, dX, N, Np, ptr<double>(h->Xs), ptr<double>(h->xsq), h->st);
+    gpx_launch_resid(dY, N, Np, O, mean_const, y_stats(h), ptr<double>(h->resid), h->st);
+    h->launches++;
     if (G == 1) {
         gpx_launch_kbuild_lower(lmat(h), nt, 0, 1, nt, ptr<double>(h->Xs), ptr<double>(h->xsq), N, d, kernel_id, variance,
-                                noise + jitter, h->st);
+                                h->rdiv, noise + jitter, h->st);
         h->launches++;
     } else {
         for (int p = next_owned_panel(h, 0); p < h->npanels; p += G) {
             gpx_launch_kbuild_lower(lmat(h), nt, panel_begin(h, p), 1, panel_end(h, p) - panel_begin(h, p), ptr<double>(h->Xs),
-                                    ptr<double>(h->xsq), N, d, kernel_id, variance, noise + jitter, h->st);
+                                    ptr<double>(h->xsq), N, d, kernel_id, variance, h->rdiv, noise + jitter, h->st);
             h->launches++;
         }
     }
     GPX_CUDA(h, cudaMemcpyAsync(h->work1.p, h->resid.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, h->st));
+    if (cap_nt > nt) {   // rows of the reserve are never touched by the solves: keep them zero
+        GPX_CUDA(h, cudaMemsetAsync(h->work2.p, 0, (size_t)Np * O * 8, h->st));
+        GPX_CUDA(h, cudaMemsetAsync(h->alpha.p, 0, (size_t)Np * O * 8, h->st));
+    }
     phase_end(h, GPX_PHASE_KBUILD);
 
     // Cholesky (+ fused forward substitution)
@@ -871,13 +640,18 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     // log-determinant and quadratic form
     if (!rc) {
         phase_begin(h, GPX_PHASE_LML);
-        gpx_launch_lml(ptr<double>(h->linv), ptr<double>(h->alpha), ptr<double>(h->resid), Np, O, ptr<double>(h->scal), h->st);
+        gpx_launch_lml(ptr<double>(h->linv), ptr<double>(h->alpha), ptr<double>(h->resid), (int64_t)nt * GPX_TILE, Np, O,
+                       ptr<double>(h->scal), h->st);
         h->launches++;
         phase_end(h, GPX_PHASE_LML);
     }
 
     double hs[2] = {0, 0};
     int hinfo = 0;
+    h->h_xstats.assign(h->fit_norm_x ? 2 * d : 0, 0.0);
+    h->h_ystats.assign(h->fit_norm_y ? 2 * O : 0, 0.0);
+    if (h->fit_norm_x) cudaMemcpyAsync(h->h_xstats.data(), h->xstats.p, (size_t)2 * d * 8, cudaMemcpyDeviceToHost, h->st);
+    if (h->fit_norm_y) cudaMemcpyAsync(h->h_ystats.data(), h->ystats.p, (size_t)2 * O * 8, cudaMemcpyDeviceToHost, h->st);
     cudaMemcpyAsync(hs, h->scal.p, 16, cudaMemcpyDeviceToHost, h->st);
     cudaMemcpyAsync(&hinfo, h->info.p, 4, cudaMemcpyDeviceToHost, h->st);
     cudaError_t e = cudaStreamSynchronize(h->st);
@@ -933,7 +707,9 @@ int gpx_lml(gpx_t* h, double* lml, double* logdet, double* quad) {
 
 // one panel step of the blocked variance solve  Tt <- Tt L^-T  for nb test tiles (rows of Tt), L operand = P
 // (upper_rows: Tt is known to be upper triangular in tile terms -- rows >= p1 are still zero -- so they are skipped)
-static void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows = false) {
+}  // extern "C"
+
+void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows) {
     const int nt = h->nt, p0 = panel_begin(h, p), p1 = panel_end(h, p);
     const int nb = (upper_rows && p1 < nb_in) ? p1 : nb_in;
     TileMat Li = linvmat(h);
@@ -961,7 +737,7 @@ static void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bo
 }
 
 // full blocked solve for one batch; world > 1 re-broadcasts the panels of L (double buffered, stream C)
-static int var_trsm(gpx_t* h, TileMat Tt, int nb) {
+int var_trsm(gpx_t* h, TileMat Tt, int nb) {
     const int np = h->npanels, G = h->world;
     if (G == 1) {
         if (nb > 0) for (int p = 0; p < np; p++) var_trsm_panel(h, Tt, nb, lmat(h), p);
@@ -988,12 +764,20 @@ static int var_trsm(gpx_t* h, TileMat Tt, int nb) {
     return 0;
 }
 
-int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int include_noise, int mem) {
+extern "C" {
+
+int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int var_cols, int include_noise,
+                int mem) {
     if (!h) return -1;
     if (!h->fitted) return fail(h, -1, "gpx_predict called before a successful gpx_fit");
     if (!Xs || !mean) return fail(h, -1, "null argument");
     if (Ns < 1) return fail(h, -1, "bad Ns");
+    if (var && var_cols != 1 && var_cols != h->O) return fail(h, -1, "var_cols must be 1 or O (%d)", h->O);
+    if (var && h->fit_norm_y && h->O > 1 && var_cols == 1)
+        return fail(h, -1, "with the output normaliser every output has its own variance scale: pass var_cols = O");
     GPX_CUDA(h, cudaSetDevice(h->device));
+    { int rcw = wait_for_caller(h); if (rcw) return rcw; }
+    if (h->world == 1 && Ns <= GPX_TILE) return gpx_predict_small(h, Xs, Ns, mean, var, var_cols, include_noise, mem);
     const int nt = h->nt, d = h->d, O = h->O, G = h->world;
     const int64_t Np = h->Np;
     for (int ph : {GPX_PHASE_PREDICT_KSTAR, GPX_PHASE_PREDICT_TRSM, GPX_PHASE_PREDICT_REDUCE, GPX_PHASE_H2D, GPX_PHASE_D2H}) h->phase_ms[ph] = 0.f;
@@ -1043,11 +827,11 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
     if (mem == GPX_MEM_HOST) {
         if ((rc = ensure(h, h->dmean, (size_t)Ns * O * 8))) return rc;
         dmean = ptr<double>(h->dmean);
-        if (var) { if ((rc = ensure(h, h->dvar, (size_t)Ns * 8))) return rc; dvar = ptr<double>(h->dvar); }
+        if (var) { if ((rc = ensure(h, h->dvar, (size_t)Ns * var_cols * 8))) return rc; dvar = ptr<double>(h->dvar); }
     }
     if (G > 1) {  // every rank fills its rows; one all-reduce assembles the result
         GPX_CUDA(h, cudaMemsetAsync(dmean, 0, (size_t)Ns * O * 8, h->st));
-        if (var) GPX_CUDA(h, cudaMemsetAsync(dvar, 0, (size_t)Ns * 8, h->st));
+        if (var) GPX_CUDA(h, cudaMemsetAsync(dvar, 0, (size_t)Ns * var_cols * 8, h->st));
     }
     if ((rc = ensure(h, h->Xt, (size_t)per * GPX_TILE * d * 8))) return rc;
     if ((rc = ensure(h, h->xtsq, (size_t)per * GPX_TILE * 8))) return rc;
@@ -1073,13 +857,13 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
         const int64_t valid = nb > 0 ? ((Ns - row0 < (int64_t)nb * GPX_TILE) ? (Ns - row0) : (int64_t)nb * GPX_TILE) : 0;
         phase_begin(h, GPX_PHASE_PREDICT_KSTAR);
         if (nb > 0) {
-            gpx_launch_scale_x(dXs + row0 * d, valid, (int64_t)nb * GPX_TILE, d, ptr<double>(h->ls), h->n_ls, ptr<double>(h->Xt),
-                               ptr<double>(h->xtsq), h->st);
+            prep_inputs(h, dXs + row0 * d, valid, (int64_t)nb * GPX_TILE, ptr<double>(h->Xt), ptr<double>(h->xtsq), h->st);
             gpx_launch_kcross(Tt, nb, per, nt, ptr<double>(h->Xt), ptr<double>(h->xtsq), valid, ptr<double>(h->Xs),
-                              ptr<double>(h->xsq), h->N, d, h->kernel_id, h->variance, ptr<double>(h->alpha), O, Np,
+                              ptr<double>(h->xsq), h->N, d, h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), O, Np,
                               ptr<double>(h->mean_partial), h->st);
-            gpx_launch_mean_reduce(ptr<double>(h->mean_partial), per, nt, O, h->mean_const, dmean, row0, row0 + valid, h->st);
-            h->launches += 3;
+            gpx_launch_mean_reduce(ptr<double>(h->mean_partial), per, nt, O, h->mean_const, y_stats(h), dmean, row0,
+                                   row0 + valid, h->st);
+            h->launches += 2;
         }
         phase_end(h, GPX_PHASE_PREDICT_KSTAR);
         if (var) {
@@ -1088,7 +872,7 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
             phase_end(h, GPX_PHASE_PREDICT_TRSM);
             phase_begin(h, GPX_PHASE_PREDICT_REDUCE);
             if (nb > 0) {
-                gpx_launch_var_reduce(Tt, nb, nt, prior_var, dvar, row0, row0 + valid, h->st);
+                gpx_launch_var_reduce(Tt, nb, nt, prior_var, y_stats(h), var_cols, dvar, row0, row0 + valid, h->st);
                 h->launches++;
             }
             phase_end(h, GPX_PHASE_PREDICT_REDUCE);
@@ -1105,12 +889,12 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
     }
     if (G > 1) {
         GPX_NCCL(h, nccl().AllReduce(dmean, dmean, (size_t)Ns * O, ncclDouble, ncclSum, h->comm, h->st));
-        if (var) GPX_NCCL(h, nccl().AllReduce(dvar, dvar, (size_t)Ns, ncclDouble, ncclSum, h->comm, h->st));
+        if (var) GPX_NCCL(h, nccl().AllReduce(dvar, dvar, (size_t)Ns * var_cols, ncclDouble, ncclSum, h->comm, h->st));
     }
     if (mem == GPX_MEM_HOST) {
         phase_begin(h, GPX_PHASE_D2H);
         GPX_CUDA(h, cudaMemcpyAsync(mean, dmean, (size_t)Ns * O * 8, cudaMemcpyDeviceToHost, h->st));
-        if (var) GPX_CUDA(h, cudaMemcpyAsync(var, dvar, (size_t)Ns * 8, cudaMemcpyDeviceToHost, h->st));
+        if (var) GPX_CUDA(h, cudaMemcpyAsync(var, dvar, (size_t)Ns * var_cols * 8, cudaMemcpyDeviceToHost, h->st));
         phase_end(h, GPX_PHASE_D2H);
     }
     cudaError_t e = cudaStreamSynchronize(h->st);
@@ -1170,14 +954,14 @@ int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double
     TileMat Tt{ptr<double>(h->Tt), ptr<int64_t>(h->tt_coloff), 0};
     TileMat Cv{ptr<double>(covt), ptr<int64_t>(covoff), 1};
     // K(X*, X) tiles + mean;  every rank handles ALL test points here (small N*), panels of L are re-broadcast
-    gpx_launch_scale_x(dXs, Ns, (int64_t)nbt * GPX_TILE, d, ptr<double>(h->ls), h->n_ls, ptr<double>(h->Xt), ptr<double>(h->xtsq), h->st);
+    prep_inputs(h, dXs, Ns, (int64_t)nbt * GPX_TILE, ptr<double>(h->Xt), ptr<double>(h->xtsq), h->st);
     gpx_launch_kcross(Tt, nbt, nbt, nt, ptr<double>(h->Xt), ptr<double>(h->xtsq), Ns, ptr<double>(h->Xs), ptr<double>(h->xsq),
-                      h->N, d, h->kernel_id, h->variance, ptr<double>(h->alpha), O, Np, ptr<double>(h->mean_partial), h->st);
-    gpx_launch_mean_reduce(ptr<double>(h->mean_partial), nbt, nt, O, h->mean_const, dmean, 0, Ns, h->st);
+                      h->N, d, h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), O, Np, ptr<double>(h->mean_partial), h->st);
+    gpx_launch_mean_reduce(ptr<double>(h->mean_partial), nbt, nt, O, h->mean_const, y_stats(h), dmean, 0, Ns, h->st);
     // K(X*, X*) + noise I (exact sigma_f^2 diagonal, like kern.K(Xnew)) into packed lower tiles
     gpx_launch_kbuild_lower(Cv, nbt, 0, 1, nbt, ptr<double>(h->Xt), ptr<double>(h->xtsq), Ns, d, h->kernel_id, h->variance,
-                            include_noise ? h->noise : 0.0, h->st);
-    h->launches += 4;
+                            h->rdiv, include_noise ? h->noise : 0.0, h->st);
+    h->launches += 3;
     if ((rc = var_trsm(h, Tt, nbt))) { cleanup(); return rc; }
     // cov -= Tt Tt^T  (lower triangle, contraction over all training tiles)
     GemmJob g{};
@@ -1246,7 +1030,7 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
         gemm(h, g, h->st);
     }
     // 3. dLML/dtheta = sum W .* dK/dtheta
-    gpx_launch_lml_grad(Ki, nt, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, h->d, h->kernel_id, h->variance,
+    gpx_launch_lml_grad(Ki, nt, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, h->d, h->kernel_id, h->variance, h->rdiv,
                         ptr<double>(h->ls), n_ls, ptr<double>(h->alpha), h->O, h->Np, ptr<double>(partial),
                         ptr<double>(gout), h->st);
     h->launches += 3;
@@ -1266,9 +1050,10 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     return nparam;
 }
 
+#ifdef GPX_ENABLE_DEBUG_API
 // Development aid (tools/gemm_bench.py): time the tile GEMM in isolation on a synthetic rectangular tile matrix.
 // C (rows x cols tiles) (-)= A (rows x ktiles) * B (cols x ktiles)^T, `reps` launches; returns the mean ms per launch.
-GPX_API double gpx_debug_gemm(gpx_t* h, int rows, int cols, int ktiles, int overwrite, int max_chunk, int reps) {
+double gpx_debug_gemm(gpx_t* h, int rows, int cols, int ktiles, int overwrite, int max_chunk, int reps) {
     if (!h || rows < 1 || cols < 1 || ktiles < 1) return -1.0;
     cudaSetDevice(h->device);
     const int ncolsA = ktiles, ncolsC = cols;
@@ -1304,7 +1089,7 @@ GPX_API double gpx_debug_gemm(gpx_t* h, int rows, int cols, int ktiles, int over
 }
 
 // Development aid: mean device time (us) of the diagonal-tile POTRF+inverse kernel on a well-conditioned SPD tile.
-GPX_API double gpx_debug_potrf(gpx_t* h, int reps) {
+double gpx_debug_potrf(gpx_t* h, int reps) {
     if (!h) return -1.0;
     cudaSetDevice(h->device);
     DevBuf src, work, inv, info;
@@ -1331,6 +1116,8 @@ GPX_API double gpx_debug_potrf(gpx_t* h, int reps) {
     for (DevBuf* b : {&src, &work, &inv, &info}) release(h, *b);
     return 1e3 * total / reps;
 }
+
+#endif  // GPX_ENABLE_DEBUG_API
 
 int gpx_export(gpx_t* h, double* alpha, double* Lout) {
     if (!h) return -1;
@@ -1360,10 +1147,11 @@ int gpx_export(gpx_t* h, double* alpha, double* Lout) {
 }
 
 int gpx_kernel_matrix(gpx_t* h, const double* X, int64_t N, int d, const double* X2, int64_t M, int kernel_id,
-                      double variance, const double* lengthscale, int n_ls, double diag_add, double* K_out) {
+                      double variance, const double* lengthscale, int n_ls, int ard, double diag_add, double* K_out) {
     if (!h) return -1;
     if (!X || !lengthscale || !K_out) return fail(h, -1, "null argument");
-    if (N < 1 || d < 1 || d > gpx_kbuild_max_d() || (n_ls != 1 && n_ls != d)) return fail(h, -1, "bad shape");
+    if (N < 1 || d < 1 || d > gpx_kbuild_max_d() || (ard ? n_ls != d : n_ls != 1)) return fail(h, -1, "bad shape");
+    const double rdiv = ard ? 1.0 : lengthscale[0];
     GPX_CUDA(h, cudaSetDevice(h->device));
     const bool sym = (X2 == nullptr);
     if (sym) M = N;
@@ -1382,20 +1170,20 @@ int gpx_kernel_matrix(gpx_t* h, const double* X, int64_t N, int d, const double*
     cudaMemcpyAsync(dX.p, X, (size_t)N * d * 8, cudaMemcpyHostToDevice, h->st);
     cudaMemcpyAsync(dls.p, lengthscale, (size_t)n_ls * 8, cudaMemcpyHostToDevice, h->st);
     cudaMemcpyAsync(off.p, co.data(), co.size() * 8, cudaMemcpyHostToDevice, h->st);
-    gpx_launch_scale_x(ptr<double>(dX), N, (int64_t)ntr * GPX_TILE, d, ptr<double>(dls), n_ls, ptr<double>(dXs), ptr<double>(dsq), h->st);
+    gpx_launch_prep_x(ptr<double>(dX), N, (int64_t)ntr * GPX_TILE, d, ptr<double>(dls), ard, nullptr, nullptr, ptr<double>(dXs), ptr<double>(dsq), h->st);
     if (sym) {
         TileMat Lm{ptr<double>(tiles), ptr<int64_t>(off), 1};
-        gpx_launch_kbuild_lower(Lm, ntr, 0, 1, ntr, ptr<double>(dXs), ptr<double>(dsq), N, d, kernel_id, variance, diag_add, h->st);
+        gpx_launch_kbuild_lower(Lm, ntr, 0, 1, ntr, ptr<double>(dXs), ptr<double>(dsq), N, d, kernel_id, variance, rdiv, diag_add, h->st);
         gpx_launch_detile(Lm, 1, N, N, ptr<double>(dense), h->st);
     } else {
         if ((rc = ensure(h, dX2, (size_t)M * d * 8)) || (rc = ensure(h, dX2s, (size_t)ntc * GPX_TILE * d * 8)) ||
             (rc = ensure(h, dsq2, (size_t)ntc * GPX_TILE * 8))) { cleanup(); return rc; }
         cudaMemcpyAsync(dX2.p, X2, (size_t)M * d * 8, cudaMemcpyHostToDevice, h->st);
-        gpx_launch_scale_x(ptr<double>(dX2), M, (int64_t)ntc * GPX_TILE, d, ptr<double>(dls), n_ls, ptr<double>(dX2s), ptr<double>(dsq2), h->st);
+        gpx_launch_prep_x(ptr<double>(dX2), M, (int64_t)ntc * GPX_TILE, d, ptr<double>(dls), ard, nullptr, nullptr, ptr<double>(dX2s), ptr<double>(dsq2), h->st);
         TileMat Tm{ptr<double>(tiles), ptr<int64_t>(off), 0};
         // rows = X (as "test"), cols = X2 (as "train")
         gpx_launch_kcross(Tm, ntr, ntr, ntc, ptr<double>(dXs), ptr<double>(dsq), N, ptr<double>(dX2s), ptr<double>(dsq2), M, d,
-                          kernel_id, variance, nullptr, 0, 0, nullptr, h->st);
+                          kernel_id, variance, rdiv, nullptr, 0, 0, nullptr, h->st);
         gpx_launch_detile(Tm, 0, N, M, ptr<double>(dense), h->st);
     }
     cudaError_t e = cudaMemcpyAsync(K_out, dense.p, (size_t)N * M * 8, cudaMemcpyDeviceToHost, h->st);

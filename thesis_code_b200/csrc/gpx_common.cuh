@@ -43,21 +43,22 @@ __device__ __forceinline__ void gpx_publish_for_async_proxy() {
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
-// stationary kernels of the scaled squared distance r2 (GPy K_of_r; src/kernels.py:4-7 of the reference)
-__device__ __forceinline__ double gpx_k_of_r2(int kernel_id, double variance, double r2) {
-    if (kernel_id == 0) {  // RBF: GPy squares sqrt(r2) again
-        double r = sqrt(r2);
+// scaled distance from the Gram-trick r^2: GPy takes the square root first and, for an isotropic kernel, divides by
+// the lengthscale afterwards (rdiv; 1.0 for ARD where the inputs were scaled before the Gram product: r / 1.0 is exact)
+__device__ __forceinline__ double gpx_scaled_r(double r2, double rdiv) { return sqrt(r2) / rdiv; }
+
+// stationary kernels of the scaled distance r (GPy K_of_r; src/kernels.py:4-7 of the reference)
+__device__ __forceinline__ double gpx_k_of_r(int kernel_id, double variance, double r) {
+    if (kernel_id == 0) {  // RBF: GPy squares the square root again
         return variance * exp(-0.5 * (r * r));
     } else if (kernel_id == 1) {  // Matern 5/2
-        double r = sqrt(r2);
         const double s5 = 2.23606797749978969641;
         return variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * exp(-s5 * r);
     } else if (kernel_id == 2) {  // Matern 3/2
-        double r = sqrt(r2);
         const double s3 = 1.73205080756887729353;
         return variance * (1.0 + s3 * r) * exp(-s3 * r);
     } else {  // Exponential
-        return variance * exp(-sqrt(r2));
+        return variance * exp(-r);
     }
 }
 
@@ -85,9 +86,13 @@ void gpx_gemm_init();  // sets the dynamic shared memory attribute
 void gpx_launch_potrf_tile(double* tile, double* inv_tile, int* info, int col_index, cudaStream_t st);
 void gpx_potrf_init();
 
-void gpx_launch_scale_x(const double* X, int64_t N, int64_t Np, int d, const double* ls, int n_ls, double* Xs,
-                        double* xsq, cudaStream_t st);
+// input loader: optional z-score (shift/scale per column, null = off), ARD lengthscale division, |x|^2 (numpy order)
+void gpx_launch_prep_x(const double* X, int64_t N, int64_t Np, int d, const double* ls, int ard, const double* shift,
+                       const double* scale, double* Xs, double* xsq, cudaStream_t st);
+// stats[0..d) = column means, stats[d..2d) = population standard deviations of the (N, d) row-major array A
+void gpx_launch_col_stats(const double* A, int64_t N, int d, double* stats, cudaStream_t st);
 // K(X*, X) tiles for `nb` test tiles (grid) laid out with `nbt_layout` test tiles per tile column (+ fused mean partials)
 void gpx_launch_kcross(TileMat Tt, int nb, int nbt_layout, int nt, const double* Xt, const double* xtsq,
                        int64_t Nt_valid, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
-                       double variance, const double* alpha, int O, int64_t Np, double* mean_partial, cudaStream_t st);
+                       double variance, double rdiv, const double* alpha, int O, int64_t Np, double* mean_partial,
+                       cudaStream_t st, double* vec_out = nullptr, int vec_rows = 0);

@@ -1,0 +1,616 @@
+// The parts of the C ABI around the core fit / predict (gpx_api.cu):
+//   * gpx_set_normalizer / gpx_get_normalizer / gpx_set_stream        (boundary plumbing)
+//   * gpx_predict_small  -- latency path of gpx_predict for <= 128 test rows
+//   * gpx_append         -- rank-k append to the resident factor        
+//   * gpx_selfcheck      -- residual / factor checks on the device      (SURVEY.md 8(d) "Parity check", C5 clause)
+//   * gpx_predict_moments-- sums behind predict_jacobian / predict_hessian
+#include "gpx_internal.cuh"
+
+namespace {
+
+// resid[o][row0 + i] = (i < k) ? Y[i][o] - mean_const : 0   for i in [0, rows_padded)
+__global__ void resid_append_kernel(const double* __restrict__ Y, int64_t k, int O, double mean_const,
+                                    double* __restrict__ resid, int64_t Np, int64_t row0, int64_t rows_padded) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows_padded * O) return;
+    int64_t o = e / rows_padded, i = e - o * rows_padded;
+    resid[o * Np + row0 + i] = (i < k) ? Y[i * O + o] - mean_const : 0.0;
+}
+
+// var[s][*] = prior - sum_i z[s][i]^2 : one CTA per test row, fixed-order tree (deterministic)
+__global__ void __launch_bounds__(256) vec_var_kernel(const double* __restrict__ z, int64_t n_rows, int64_t Np, double prior,
+                                                      const double* __restrict__ ystats, int var_cols,
+                                                      double* __restrict__ var) {
+    __shared__ double red[256];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const double* zs = z + (int64_t)s * Np;
+    double a = 0.0;
+    for (int64_t i = tid; i < n_rows; i += 256) a = fma(zs[i], zs[i], a);
+    red[tid] = a;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
+    if (tid < var_cols) {
+        const double v = prior - red[0];
+        const double sd = ystats ? ystats[var_cols + tid] : 1.0;
+        var[(int64_t)s * var_cols + tid] = ystats ? v * (sd * sd) : v;
+    }
+}
+
+// v[i] = fixed pseudo-random value in (-1, 1) for i < N, 0 for the padding (splitmix64 of the index)
+__global__ void fill_random_kernel(double* __restrict__ v, int64_t N, int64_t Np) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    uint64_t x = (uint64_t)i + 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    v[i] = i < N ? ((double)(x >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0 : 0.0;
+}
+
+// y (+)= op(L) x over the owned tile columns of the packed lower factor (check code: atomics, not deterministic).
+//   trans = 0:  y_I += L_IJ x_J ;  trans = 1:  y_J += L_IJ^T x_I.   grid (nt, ncols); column ordinal -> J as in GemmJob.
+__global__ void __launch_bounds__(256) tri_matvec_kernel(TileMat L, int nt, int jbase, int jW, int jstride,
+                                                         const double* __restrict__ x, double* __restrict__ y, int trans) {
+    const int I = blockIdx.x, m = blockIdx.y;
+    const int J = jbase + (m / jW) * jstride + (m % jW);
+    if (J >= nt || I < J) return;
+    __shared__ double sx[GPX_TILE];
+    const int tid = threadIdx.x, q = tid & 127, half = tid >> 7;
+    if (tid < GPX_TILE) sx[tid] = x[(int64_t)(trans ? I : J) * GPX_TILE + tid];
+    __syncthreads();
+    const double* tp = tile_ptr(L, I, J);
+    double s = 0.0;
+    if (!trans) {   // row q of the tile, columns of chunks half*8 .. half*8+7 (lower triangle only on the diagonal tile)
+        for (int c = half * 64; c < half * 64 + 64; c++) {
+            if (I == J && c > q) break;
+            s = fma(tp[gpx_tile_idx(q, c)], sx[c], s);
+        }
+        atomicAdd(y + (int64_t)I * GPX_TILE + q, s);
+    } else {        // column q of the tile, rows half*64 .. half*64+63
+        for (int r = half * 64; r < half * 64 + 64; r++) {
+            if (I == J && r < q) continue;
+            s = fma(tp[gpx_tile_idx(r, q)], sx[r], s);
+        }
+        atomicAdd(y + (int64_t)J * GPX_TILE + q, s);
+    }
+}
+
+// out[0] = sum (a + c * b - t)^2, out[1] = sum t^2   (a = K x, b = x, c = noise + jitter, t = target); one CTA
+__global__ void __launch_bounds__(1024) resid_norm_kernel(const double* __restrict__ a, const double* __restrict__ b, double c,
+                                                          const double* __restrict__ t, int64_t n, double* __restrict__ out) {
+    __shared__ double red[2][32];
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double r = a[i] + c * b[i] - t[i];
+        s0 = fma(r, r, s0);
+        s1 = fma(t[i], t[i], s1);
+    }
+    for (int off = 16; off > 0; off >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x0 = 0.0, x1 = 0.0;
+        for (int w = 0; w < 32; w++) { x0 += red[0][w]; x1 += red[1][w]; }
+        out[0] = x0; out[1] = x1;
+    }
+}
+
+// t = a + c * b
+__global__ void axpy_kernel(const double* __restrict__ a, const double* __restrict__ b, double c, double* __restrict__ t, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i] = a[i] + c * b[i];
+}
+
+// Moments of the posterior mean (see gpx.h: gpx_predict_moments).  One CTA per test point, 256 training points per
+// step: phase A evaluates w_j = k(x_j, x*) alpha_j (one per thread, the K-build's own Gram-trick arithmetic), phase B
+// lets thread m accumulate moment m over the step's 256 points in index order (deterministic).
+__global__ void __launch_bounds__(256) moments_kernel(const double* __restrict__ Xt, const double* __restrict__ xtsq,
+                                                      const double* __restrict__ Xs, const double* __restrict__ xsq, int64_t N,
+                                                      int d, int kernel_id, double variance, double rdiv,
+                                                      const double* __restrict__ alpha, double* __restrict__ S0,
+                                                      double* __restrict__ S1, double* __restrict__ S2) {
+    extern __shared__ __align__(16) double sm[];
+    double* w = sm;                 // [256]
+    double* xi = w + 256;           // [d]
+    double* xj = xi + d;            // [256][d]
+    const int i = blockIdx.x, tid = threadIdx.x;
+    for (int k = tid; k < d; k += 256) xi[k] = Xt[(int64_t)i * d + k];
+    const double xisq = xtsq[i];
+    const int M = 1 + (S1 ? d : 0) + (S2 ? d * d : 0);
+    constexpr int kMaxPer = 5;      // moments per thread: 256 * 5 >= 1 + 32 + 32^2 ... capped by the host check d <= 32 -> 1057 < 1280
+    double acc[kMaxPer];
+#pragma unroll
+    for (int u = 0; u < kMaxPer; u++) acc[u] = 0.0;
+    __syncthreads();
+    for (int64_t j0 = 0; j0 < N; j0 += 256) {
+        const int64_t j = j0 + tid;
+        double wj = 0.0;
+        if (j < N) {
+            double dot = 0.0;
+            for (int k = 0; k < d; k++) { const double v = Xs[j * d + k]; xj[tid * d + k] = v; dot = fma(xi[k], v, dot); }
+            const double r2 = fmax(-2.0 * dot + (xisq + xsq[j]), 0.0);
+            wj = gpx_k_of_r(kernel_id, variance, gpx_scaled_r(r2, rdiv)) * alpha[j];
+        }
+        w[tid] = wj;
+        __syncthreads();
+        const int cnt = (N - j0) < 256 ? (int)(N - j0) : 256;
+#pragma unroll
+        for (int u = 0; u < kMaxPer; u++) {
+            const int m = tid + u * 256;
+            if (m >= M) break;
+            double a = acc[u];
+            if (m == 0) {
+                for (int jj = 0; jj < cnt; jj++) a += w[jj];
+            } else if (S1 && m <= d) {
+                const int k = m - 1;
+                for (int jj = 0; jj < cnt; jj++) a = fma(w[jj], xi[k] - xj[jj * d + k], a);
+            } else {
+                const int e = m - 1 - (S1 ? d : 0), k = e / d, l = e - k * d;
+                for (int jj = 0; jj < cnt; jj++) a = fma(w[jj], (xi[k] - xj[jj * d + k]) * (xi[l] - xj[jj * d + l]), a);
+            }
+            acc[u] = a;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < kMaxPer; u++) {
+        const int m = tid + u * 256;
+        if (m >= M) break;
+        if (m == 0) S0[i] = acc[u];
+        else if (S1 && m <= d) S1[(int64_t)i * d + (m - 1)] = acc[u];
+        else S2[(int64_t)i * d * d + (m - 1 - (S1 ? d : 0))] = acc[u];
+    }
+}
+
+constexpr int kMomentsMaxD = 32;
+size_t moments_smem(int d) { return (size_t)(256 + d + 256 * d) * sizeof(double); }
+
+// ---- host helpers --------------------------------------------------------------------------------------------------
+
+struct SmallWs {   // views into h->sp (one allocation, re-made when cap_nt / d / O change)
+    double *Xin, *Xt, *xtsq, *mean_partial, *b, *z, *mean, *var;
+};
+constexpr int kVecRows = 8;   // variance of <= 8 rows: GEMV-style substitution; above: one tile row through the DMMA solve
+
+SmallWs small_views(gpx_t* h) {
+    const int64_t d = h->d, O = h->O, Np = h->Np, cap = h->cap_nt;
+    double* p = ptr<double>(h->sp);
+    SmallWs w;
+    w.Xin = p; p += GPX_TILE * d;
+    w.Xt = p; p += GPX_TILE * d;
+    w.xtsq = p; p += GPX_TILE;
+    w.mean_partial = p; p += cap * GPX_TILE * O;
+    w.b = p; p += kVecRows * Np;
+    w.z = p; p += kVecRows * Np;
+    w.mean = p; p += GPX_TILE * O;
+    w.var = p; p += GPX_TILE * O;
+    return w;
+}
+
+int small_workspace(gpx_t* h) {
+    const int64_t d = h->d, O = h->O, Np = h->Np, cap = h->cap_nt;
+    const size_t doubles = (size_t)(2 * GPX_TILE * d + GPX_TILE + cap * GPX_TILE * O + 2 * kVecRows * Np + 2 * GPX_TILE * O);
+    if (h->sp.p && h->sp_key[0] == cap && h->sp_key[1] == d && h->sp_key[2] == O) return 0;
+    release(h, h->sp);
+    int rc = ensure(h, h->sp, doubles * 8);
+    if (rc) return rc;
+    h->sp_key[0] = cap; h->sp_key[1] = d; h->sp_key[2] = O;
+    h->gen++;   // captured graphs point into the old workspace
+    const size_t pin_bytes = (size_t)(GPX_TILE * d + 2 * GPX_TILE * O) * 8;
+    if (h->pin_bytes < pin_bytes) {
+        if (h->pin) cudaFreeHost(h->pin);
+        h->pin = nullptr; h->pin_bytes = 0;
+        GPX_CUDA(h, cudaHostAlloc(&h->pin, pin_bytes, cudaHostAllocDefault));
+        h->pin_bytes = pin_bytes;
+    }
+    return 0;
+}
+
+// the graph-capturable part of the latency path: loader -> K* (+ mean partials, + right-hand-side vectors) -> mean
+// -> [forward substitution -> variance].  Returns the number of kernels launched.
+int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_cols, int include_noise, cudaStream_t st) {
+    const int nt = h->nt, d = h->d, O = h->O;
+    const int64_t Np = h->Np;
+    int n = 0;
+    gpx_launch_prep_x(w.Xin, Ns, GPX_TILE, d, ptr<double>(h->ls), h->ard, x_shift(h), x_scale(h), w.Xt, w.xtsq, st); n++;
+    gpx_launch_kcross(TileMat{nullptr, nullptr, 0}, 1, 1, nt, w.Xt, w.xtsq, Ns, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, d,
+                      h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), O, Np, w.mean_partial, st,
+                      want_var ? w.b : nullptr, (int)Ns); n++;
+    gpx_launch_mean_reduce(w.mean_partial, 1, nt, O, h->mean_const, y_stats(h), w.mean, 0, Ns, st); n++;
+    if (want_var) {
+        for (int J = 0; J < nt; J++) {
+            gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, w.b, w.z, Np, (int)Ns, 2 * h->num_sms, st); n++;
+        }
+        const double prior = h->variance + (include_noise ? h->noise : 0.0);
+        vec_var_kernel<<<(int)Ns, 256, 0, st>>>(w.z, (int64_t)nt * GPX_TILE, Np, prior, y_stats(h), var_cols, w.var); n++;
+    }
+    return n;
+}
+
+struct GraphKey { uint64_t gen; int64_t Ns; int want_var, var_cols, include_noise; };
+
+// column-packed factor storage for `cap` tile rows: offsets of all columns (single GPU: every column is owned)
+int64_t packed_offsets(int cap, std::vector<int64_t>& off) {
+    off.resize(cap);
+    int64_t o = 0;
+    for (int c = 0; c < cap; c++) { off[c] = o; o += (int64_t)(cap - c) * GPX_TILE_ELEMS; }
+    return o;
+}
+
+// re-lay the factor and the vectors out for new_cap tile rows (gpx_append ran out of reserve)
+int relayout(gpx_t* h, int new_cap) {
+    const int nt = h->nt, O = h->O, d = h->d;
+    const int64_t oldNp = h->Np, newNp = (int64_t)new_cap * GPX_TILE, rows = (int64_t)nt * GPX_TILE;
+    std::vector<int64_t> noff, lc(new_cap);
+    const int64_t elems = packed_offsets(new_cap, noff);
+    for (int c = 0; c < new_cap; c++) lc[c] = (int64_t)c * GPX_TILE_ELEMS;
+    DevBuf nL, nlinv, nXs, nxsq, nres, nw1, nw2, nal, ncoloff, nlcoloff;
+    int rc;
+    auto bail = [&](int code) { for (DevBuf* b : {&nL, &nlinv, &nXs, &nxsq, &nres, &nw1, &nw2, &nal, &ncoloff, &nlcoloff}) release(h, *b); return code; };
+    if ((rc = ensure(h, nL, (size_t)elems * 8)) || (rc = ensure(h, nlinv, (size_t)new_cap * GPX_TILE_BYTES)) ||
+        (rc = ensure(h, nXs, (size_t)newNp * d * 8)) || (rc = ensure(h, nxsq, (size_t)newNp * 8)) ||
+        (rc = ensure(h, nres, (size_t)newNp * O * 8)) || (rc = ensure(h, nw1, (size_t)newNp * O * 8)) ||
+        (rc = ensure(h, nw2, (size_t)newNp * O * 8)) || (rc = ensure(h, nal, (size_t)newNp * O * 8)) ||
+        (rc = ensure(h, ncoloff, (size_t)new_cap * 8)) || (rc = ensure(h, nlcoloff, (size_t)new_cap * 8))) return bail(rc);
+    cudaStream_t st = h->st;
+    for (int c = 0; c < nt; c++)
+        GPX_CUDA(h, cudaMemcpyAsync(ptr<double>(nL) + noff[c], ptr<double>(h->L) + h->h_coloff[c], (size_t)(nt - c) * GPX_TILE_BYTES,
+                                    cudaMemcpyDeviceToDevice, st));
+    GPX_CUDA(h, cudaMemcpyAsync(nlinv.p, h->linv.p, (size_t)nt * GPX_TILE_BYTES, cudaMemcpyDeviceToDevice, st));
+    GPX_CUDA(h, cudaMemsetAsync(nXs.p, 0, nXs.bytes, st));
+    GPX_CUDA(h, cudaMemsetAsync(nxsq.p, 0, nxsq.bytes, st));
+    GPX_CUDA(h, cudaMemcpyAsync(nXs.p, h->Xs.p, (size_t)rows * d * 8, cudaMemcpyDeviceToDevice, st));
+    GPX_CUDA(h, cudaMemcpyAsync(nxsq.p, h->xsq.p, (size_t)rows * 8, cudaMemcpyDeviceToDevice, st));
+    DevBuf* olds[] = {&h->resid, &h->work1, &h->work2, &h->alpha};
+    DevBuf* news[] = {&nres, &nw1, &nw2, &nal};
+    for (int i = 0; i < 4; i++) {
+        GPX_CUDA(h, cudaMemsetAsync(news[i]->p, 0, news[i]->bytes, st));
+        GPX_CUDA(h, cudaMemcpy2DAsync(news[i]->p, (size_t)newNp * 8, olds[i]->p, (size_t)oldNp * 8, (size_t)rows * 8, (size_t)O,
+                                      cudaMemcpyDeviceToDevice, st));
+    }
+    GPX_CUDA(h, cudaMemcpyAsync(ncoloff.p, noff.data(), (size_t)new_cap * 8, cudaMemcpyHostToDevice, st));
+    GPX_CUDA(h, cudaMemcpyAsync(nlcoloff.p, lc.data(), (size_t)new_cap * 8, cudaMemcpyHostToDevice, st));
+    GPX_CUDA(h, cudaStreamSynchronize(st));
+    auto swap_in = [&](DevBuf& dst, DevBuf& src) { release(h, dst); dst = src; src = DevBuf(); };
+    swap_in(h->L, nL); swap_in(h->linv, nlinv); swap_in(h->Xs, nXs); swap_in(h->xsq, nxsq);
+    swap_in(h->resid, nres); swap_in(h->work1, nw1); swap_in(h->work2, nw2); swap_in(h->alpha, nal);
+    swap_in(h->coloff, ncoloff); swap_in(h->linv_coloff, nlcoloff);
+    h->h_coloff = noff;
+    h->cap_nt = new_cap;
+    h->Np = newNp;
+    h->gen++;
+    return 0;
+}
+
+// out[row tiles t0..t1) = K(X, X) vec  (K rebuilt tile by tile with the cross-kernel builder; vec, out: [Np])
+int kmatvec(gpx_t* h, const double* vec, double* out, DevBuf& partial, int t0, int t1) {
+    const int nt = h->nt, d = h->d;
+    const int nbmax = 64;
+    int rc = ensure(h, partial, (size_t)nt * nbmax * GPX_TILE * 8);
+    if (rc) return rc;
+    for (int t = t0; t < t1; t += nbmax) {
+        const int nb = (t1 - t < nbmax) ? (t1 - t) : nbmax;
+        const int64_t row0 = (int64_t)t * GPX_TILE;
+        int64_t valid = h->N - row0;
+        if (valid > (int64_t)nb * GPX_TILE) valid = (int64_t)nb * GPX_TILE;
+        if (valid < 0) valid = 0;
+        gpx_launch_kcross(TileMat{nullptr, nullptr, 0}, nb, nb, nt, ptr<double>(h->Xs) + row0 * d, ptr<double>(h->xsq) + row0, valid,
+                          ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, d, h->kernel_id, h->variance, h->rdiv, vec, 1, h->Np,
+                          ptr<double>(partial), h->st);
+        gpx_launch_mean_reduce(ptr<double>(partial), nb, nt, 1, 0.0, nullptr, out, row0, row0 + (int64_t)nb * GPX_TILE, h->st);
+        h->launches += 2;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================================================================
+int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int var_cols, int include_noise,
+                      int mem) {
+    const int nt = h->nt, d = h->d, O = h->O;
+    for (int ph : {GPX_PHASE_PREDICT_KSTAR, GPX_PHASE_PREDICT_TRSM, GPX_PHASE_PREDICT_REDUCE, GPX_PHASE_H2D, GPX_PHASE_D2H}) h->phase_ms[ph] = 0.f;
+    int rc = small_workspace(h);
+    if (rc) return rc;
+    const SmallWs w = small_views(h);
+    cudaStream_t st = h->st;
+    double* pin = reinterpret_cast<double*>(h->pin);
+    if (mem == GPX_MEM_HOST) {
+        memcpy(pin, Xs, (size_t)Ns * d * 8);
+        GPX_CUDA(h, cudaMemcpyAsync(w.Xin, pin, (size_t)Ns * d * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        GPX_CUDA(h, cudaMemcpyAsync(w.Xin, Xs, (size_t)Ns * d * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    const bool want_var = var != nullptr;
+    if (!want_var || Ns <= kVecRows) {
+        if (h->predict_graph) {
+            // replay (or capture once per fit generation and shape) the whole launch chain as one CUDA graph
+            gpx_handle::SmallGraph* g = nullptr;
+            for (auto& e : h->graphs)
+                if (e.gen == h->gen && e.Ns == Ns && e.want_var == (int)want_var && e.var_cols == var_cols && e.include_noise == include_noise) g = &e;
+            if (!g) {
+                for (auto it = h->graphs.begin(); it != h->graphs.end();) {   // drop stale generations, bound the cache
+                    if (it->gen != h->gen || h->graphs.size() >= 8) { cudaGraphExecDestroy(it->exec); it = h->graphs.erase(it); }
+                    else ++it;
+                }
+                cudaGraph_t graph = nullptr;
+                GPX_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const int nodes = small_chain(h, w, Ns, want_var, var_cols, include_noise, st);
+                cudaError_t ec = cudaStreamEndCapture(st, &graph);
+                if (ec != cudaSuccess || !graph) { cudaGetLastError(); return fail(h, -2, "CUDA graph capture of the predict chain failed: %s", cudaGetErrorString(ec)); }
+                gpx_handle::SmallGraph e{};
+                e.gen = h->gen; e.Ns = Ns; e.want_var = want_var; e.var_cols = var_cols; e.include_noise = include_noise; e.nodes = nodes;
+                ec = cudaGraphInstantiate(&e.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ec != cudaSuccess) { cudaGetLastError(); return fail(h, -2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ec)); }
+                h->graphs.push_back(e);
+                g = &h->graphs.back();
+            }
+            GPX_CUDA(h, cudaGraphLaunch(g->exec, st));
+            h->launches += g->nodes;
+        } else {
+            h->launches += small_chain(h, w, Ns, want_var, var_cols, include_noise, st);
+        }
+    } else {
+        // 9..128 rows with variance: one tile row through the blocked DMMA solve (workspace kept between calls)
+        if ((rc = ensure(h, h->Tt, (size_t)h->cap_nt * GPX_TILE_BYTES))) return rc;
+        TileMat Tt{ptr<double>(h->Tt), ptr<int64_t>(h->linv_coloff), 0};   // one tile row: column c at c * 128 * 128
+        gpx_launch_prep_x(w.Xin, Ns, GPX_TILE, d, ptr<double>(h->ls), h->ard, x_shift(h), x_scale(h), w.Xt, w.xtsq, st);
+        gpx_launch_kcross(Tt, 1, 1, nt, w.Xt, w.xtsq, Ns, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, d, h->kernel_id, h->variance,
+                          h->rdiv, ptr<double>(h->alpha), O, h->Np, w.mean_partial, st);
+        gpx_launch_mean_reduce(w.mean_partial, 1, nt, O, h->mean_const, y_stats(h), w.mean, 0, Ns, st);
+        h->launches += 3;
+        if ((rc = var_trsm(h, Tt, 1))) return rc;
+        gpx_launch_var_reduce(Tt, 1, nt, h->variance + (include_noise ? h->noise : 0.0), y_stats(h), var_cols, w.var, 0, Ns, st);
+        h->launches++;
+    }
+    const size_t mb = (size_t)Ns * O * 8, vb = want_var ? (size_t)Ns * var_cols * 8 : 0;
+    if (mem == GPX_MEM_HOST) {
+        GPX_CUDA(h, cudaMemcpyAsync(pin, w.mean, mb, cudaMemcpyDeviceToHost, st));
+        if (want_var) GPX_CUDA(h, cudaMemcpyAsync(pin + GPX_TILE * O, w.var, vb, cudaMemcpyDeviceToHost, st));
+    } else {
+        GPX_CUDA(h, cudaMemcpyAsync(mean, w.mean, mb, cudaMemcpyDeviceToDevice, st));
+        if (want_var) GPX_CUDA(h, cudaMemcpyAsync(var, w.var, vb, cudaMemcpyDeviceToDevice, st));
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, -2, "CUDA error during predict (latency path): %s", cudaGetErrorString(e));
+    if (mem == GPX_MEM_HOST) {
+        memcpy(mean, pin, mb);
+        if (want_var) memcpy(var, pin + GPX_TILE * O, vb);
+    }
+    gemm_collect(h);
+    return 0;
+}
+
+extern "C" {
+
+int gpx_set_normalizer(gpx_t* h, int normalize_input, int normalize_output) {
+    if (!h) return -1;
+    h->norm_x = normalize_input ? 1 : 0;
+    h->norm_y = normalize_output ? 1 : 0;
+    return 0;
+}
+
+int gpx_get_normalizer(gpx_t* h, double* x_mean, double* x_std, double* y_mean, double* y_std) {
+    if (!h) return -1;
+    if (!h->fitted) return fail(h, -1, "gpx_get_normalizer called before a successful gpx_fit");
+    const int d = h->d, O = h->O;
+    for (int k = 0; k < d; k++) {
+        if (x_mean) x_mean[k] = h->fit_norm_x ? h->h_xstats[k] : 0.0;
+        if (x_std) x_std[k] = h->fit_norm_x ? h->h_xstats[d + k] : 1.0;
+    }
+    for (int o = 0; o < O; o++) {
+        if (y_mean) y_mean[o] = h->fit_norm_y ? h->h_ystats[o] : 0.0;
+        if (y_std) y_std[o] = h->fit_norm_y ? h->h_ystats[O + o] : 1.0;
+    }
+    return 0;
+}
+
+int gpx_set_stream(gpx_t* h, void* stream, int has_stream) {
+    if (!h) return -1;
+    h->caller_stream = reinterpret_cast<cudaStream_t>(stream);
+    h->has_caller_stream = has_stream != 0;
+    return 0;
+}
+
+int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem) {
+    if (!h) return -1;
+    if (!h->fitted) return fail(h, -1, "gpx_append called before a successful gpx_fit");
+    if (!Xn || !Yn || k < 1) return fail(h, -1, "bad argument");
+    if (h->world > 1) return fail(h, -8, "gpx_append: not available on a sharded handle (refit)");
+    if (h->fit_norm_x || h->fit_norm_y) return fail(h, -8, "gpx_append: the normaliser statistics change with the data (refit)");
+    GPX_CUDA(h, cudaSetDevice(h->device));
+    { int rcw = wait_for_caller(h); if (rcw) return rcw; }
+    const int d = h->d, O = h->O, W = h->W;
+    const int64_t N0 = h->N, N1 = N0 + k;
+    const int t0 = (int)(N0 / GPX_TILE), nt1 = (int)((N1 + GPX_TILE - 1) / GPX_TILE);
+    int rc;
+    if (nt1 > h->cap_nt) {
+        int grow = h->cap_nt / 4 > 1 ? h->cap_nt / 4 : 1;
+        int new_cap = h->cap_nt + grow > nt1 ? h->cap_nt + grow : nt1;
+        if ((rc = relayout(h, new_cap))) return rc;
+    }
+    h->fitted = false;   // until the append has succeeded
+    cudaStream_t st = h->st;
+    const double *dX, *dY;
+    DevBuf stageY;
+    if ((rc = to_device(h, Xn, (size_t)k * d, mem, h->stage, &dX))) return rc;
+    if ((rc = to_device(h, Yn, (size_t)k * O, mem, stageY, &dY))) { release(h, stageY); return rc; }
+    const int64_t Np = h->Np, rows_padded = (int64_t)nt1 * GPX_TILE - N0;
+    prep_inputs(h, dX, k, rows_padded, ptr<double>(h->Xs) + N0 * d, ptr<double>(h->xsq) + N0, st);
+    resid_append_kernel<<<(int)((rows_padded * O + 255) / 256), 256, 0, st>>>(dY, k, O, h->mean_const, ptr<double>(h->resid), Np, N0,
+                                                                            rows_padded);
+    h->launches++;
+    h->N = N1; h->nt = nt1; h->npanels = (nt1 + W - 1) / W;
+    h->gen++;
+    GPX_CUDA(h, cudaMemsetAsync(h->info.p, 0, 64, st));
+    // 1. the new rows of Ky (tile rows t0 .. nt1-1; a partially filled tile row t0 is rebuilt whole)
+    gpx_launch_kbuild_rows(lmat(h), nt1, t0, ptr<double>(h->Xs), ptr<double>(h->xsq), N1, d, h->kernel_id, h->variance, h->rdiv,
+                           h->noise + h->jitter, st);
+    h->launches++;
+    // 2. solve them against the resident factor: L(R, J) = (K(R, J) - sum_{k<J} L(R,k) L(J,k)^T) Linv_J^T for J < t0, and
+    //    subtract their outer product from the new diagonal block -- panel by panel, exactly the predictive-variance solve
+    TileMat L = lmat(h), Li = linvmat(h);
+    for (int c0 = 0; c0 < t0; c0 += W) {
+        const int c1 = c0 + W < t0 ? c0 + W : t0;
+        for (int c = c0; c < c1; c++) {
+            GemmJob t{};
+            t.A = L; t.B = Li; t.C = L;
+            t.tri = 0; t.i0 = t0; t.i1 = nt1; t.ncols = 1; t.jbase = c; t.jW = GPX_JW_CONTIG; t.jstride = 0;
+            t.k0 = c; t.k1 = c + 1; t.bdiag = 1; t.overwrite = 1;
+            gemm(h, t, st);
+            if (c + 1 < c1) {
+                GemmJob u{};
+                u.A = L; u.B = L; u.C = L;
+                u.tri = 0; u.i0 = t0; u.i1 = nt1; u.ncols = c1 - (c + 1); u.jbase = c + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+                u.k0 = c; u.k1 = c + 1; u.bdiag = 0; u.overwrite = 0;
+                gemm(h, u, st);
+            }
+        }
+        if (c1 < t0) {
+            GemmJob u{};
+            u.A = L; u.B = L; u.C = L;
+            u.tri = 0; u.i0 = t0; u.i1 = nt1; u.ncols = t0 - c1; u.jbase = c1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+            u.k0 = c0; u.k1 = c1; u.bdiag = 0; u.overwrite = 0;
+            gemm(h, u, st);
+        }
+        GemmJob s{};
+        s.A = L; s.B = L; s.C = L;
+        s.tri = 1; s.i0 = t0; s.i1 = nt1; s.ncols = nt1 - t0; s.jbase = t0; s.jW = GPX_JW_CONTIG; s.jstride = 0;
+        s.k0 = c0; s.k1 = c1; s.bdiag = 0; s.overwrite = 0;
+        gemm(h, s, st);
+    }
+    // 3. Cholesky of the Schur complement (the new diagonal block)
+    factor_cols(h, t0, nt1, nt1, st);
+    // 4. alpha and the LML: two substitutions over the whole factor
+    GPX_CUDA(h, cudaMemcpyAsync(h->work1.p, h->resid.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
+    for (int J = 0; J < nt1; J++) {
+        gpx_launch_fwd_step(L, ptr<double>(h->linv), nt1, J, ptr<double>(h->work1), ptr<double>(h->work2), Np, O, 2 * h->num_sms, st);
+        h->launches++;
+    }
+    rc = backward_solve(h);
+    gpx_launch_lml(ptr<double>(h->linv), ptr<double>(h->alpha), ptr<double>(h->resid), (int64_t)nt1 * GPX_TILE, Np, O,
+                   ptr<double>(h->scal), st);
+    h->launches++;
+    double hs[2] = {0, 0};
+    int hinfo = 0;
+    cudaMemcpyAsync(hs, h->scal.p, 16, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&hinfo, h->info.p, 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    release(h, stageY);
+    if (rc) return rc;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, -2, "CUDA error during append: %s", cudaGetErrorString(e));
+    gemm_collect(h);
+    if (hinfo != 0) {
+        fail(h, hinfo, "append: Ky is not positive definite: non-positive pivot at row %d", hinfo);
+        return hinfo;
+    }
+    h->logdet = hs[0];
+    h->quad = hs[1];
+    const double log2pi = 1.8378770664093454835606594728112;
+    h->lml = 0.5 * (-(double)N1 * O * log2pi - (double)O * h->logdet - h->quad);
+    h->fitted = true;
+    return 0;
+}
+
+int gpx_selfcheck(gpx_t* h, double* out, int capacity) {
+    if (!h) return -1;
+    if (!h->fitted) return fail(h, -1, "gpx_selfcheck called before a successful gpx_fit");
+    if (!out || capacity < 4) return fail(h, -1, "output buffer too small: need 4");
+    GPX_CUDA(h, cudaSetDevice(h->device));
+    const int nt = h->nt, G = h->world, W = h->W;
+    const int64_t Np = h->Np, n = (int64_t)nt * GPX_TILE;
+    const double c = h->noise + h->jitter;
+    cudaStream_t st = h->st;
+    DevBuf partial, ka, v, w, u, kv, tgt, sc;
+    int rc = 0;
+    auto cleanup = [&]() { for (DevBuf* b : {&partial, &ka, &v, &w, &u, &kv, &tgt, &sc}) release(h, *b); };
+    if ((rc = ensure(h, ka, (size_t)Np * 8)) || (rc = ensure(h, v, (size_t)Np * 8)) || (rc = ensure(h, w, (size_t)Np * 8)) ||
+        (rc = ensure(h, u, (size_t)Np * 8)) || (rc = ensure(h, kv, (size_t)Np * 8)) || (rc = ensure(h, tgt, (size_t)Np * 8)) ||
+        (rc = ensure(h, sc, 64))) { cleanup(); return rc; }
+    // rows of the K mat-vecs are sharded over the ranks like the test tiles of gpx_predict
+    const int t0 = (int)((int64_t)nt * h->rank / G), t1 = (int)((int64_t)nt * (h->rank + 1) / G);
+    auto allreduce = [&](DevBuf& b) -> int {
+        if (G > 1) GPX_NCCL(h, nccl().AllReduce(b.p, b.p, (size_t)Np, ncclDouble, ncclSum, h->comm, st));
+        return 0;
+    };
+    // (a) || Ky alpha - (y - m) || / || y - m ||   (first output)
+    GPX_CUDA(h, cudaMemsetAsync(ka.p, 0, (size_t)Np * 8, st));
+    if ((rc = kmatvec(h, ptr<double>(h->alpha), ptr<double>(ka), partial, t0, t1)) || (rc = allreduce(ka))) { cleanup(); return rc; }
+    resid_norm_kernel<<<1, 1024, 0, st>>>(ptr<double>(ka), ptr<double>(h->alpha), c, ptr<double>(h->resid), n, ptr<double>(sc));
+    // (b) || L (L^T v) - Ky v || / || Ky v ||
+    fill_random_kernel<<<(int)((Np + 255) / 256), 256, 0, st>>>(ptr<double>(v), h->N, Np);
+    GPX_CUDA(h, cudaMemsetAsync(w.p, 0, (size_t)Np * 8, st));
+    GPX_CUDA(h, cudaMemsetAsync(u.p, 0, (size_t)Np * 8, st));
+    GPX_CUDA(h, cudaMemsetAsync(kv.p, 0, (size_t)Np * 8, st));
+    const int q0 = next_owned_panel(h, 0);
+    const int ncols = q0 < h->npanels ? owned_cols_from(h, q0) : 0;
+    const int jbase = q0 < h->npanels ? panel_begin(h, q0) : 0;
+    if (ncols > 0) tri_matvec_kernel<<<dim3(nt, ncols), 256, 0, st>>>(lmat(h), nt, jbase, W, W * G, ptr<double>(v), ptr<double>(w), 1);
+    if ((rc = allreduce(w))) { cleanup(); return rc; }
+    if (ncols > 0) tri_matvec_kernel<<<dim3(nt, ncols), 256, 0, st>>>(lmat(h), nt, jbase, W, W * G, ptr<double>(w), ptr<double>(u), 0);
+    if ((rc = allreduce(u))) { cleanup(); return rc; }
+    if ((rc = kmatvec(h, ptr<double>(v), ptr<double>(kv), partial, t0, t1)) || (rc = allreduce(kv))) { cleanup(); return rc; }
+    axpy_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(ptr<double>(kv), ptr<double>(v), c, ptr<double>(tgt), n);
+    // || u - tgt ||: reuse resid_norm with a = u, b = anything, c = 0
+    resid_norm_kernel<<<1, 1024, 0, st>>>(ptr<double>(u), ptr<double>(u), 0.0, ptr<double>(tgt), n, ptr<double>(sc) + 2);
+    h->launches += 6;
+    double hs[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(hs, sc.p, 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) return fail(h, -2, "CUDA error in gpx_selfcheck: %s", cudaGetErrorString(e));
+    out[0] = hs[1] > 0 ? sqrt(hs[0] / hs[1]) : 0.0;
+    out[1] = hs[3] > 0 ? sqrt(hs[2] / hs[3]) : 0.0;
+    out[2] = sqrt(hs[3]);
+    out[3] = sqrt(hs[1]);
+    return 0;
+}
+
+int gpx_predict_moments(gpx_t* h, const double* Xs, int64_t Ns, double* S0, double* S1, double* S2, int mem) {
+    if (!h) return -1;
+    if (!h->fitted) return fail(h, -1, "gpx_predict_moments called before a successful gpx_fit");
+    if (!Xs || !S0 || Ns < 1) return fail(h, -1, "bad argument");
+    if (h->world > 1) return fail(h, -6, "gpx_predict_moments: single-GPU handles only");
+    const int d = h->d;
+    if (d > kMomentsMaxD) return fail(h, -1, "gpx_predict_moments supports input dimension <= %d", kMomentsMaxD);
+    GPX_CUDA(h, cudaSetDevice(h->device));
+    { int rcw = wait_for_caller(h); if (rcw) return rcw; }
+    cudaStream_t st = h->st;
+    static bool attr_done[64] = {false};
+    if (h->device < 64 && !attr_done[h->device]) {
+        cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moments_smem(kMomentsMaxD));
+        attr_done[h->device] = true;
+    }
+    int rc;
+    const double* dXs;
+    if ((rc = to_device(h, Xs, (size_t)Ns * d, mem, h->stage, &dXs))) return rc;
+    DevBuf xt, xtsq, o0, o1, o2;
+    auto cleanup = [&]() { for (DevBuf* b : {&xt, &xtsq, &o0, &o1, &o2}) release(h, *b); };
+    if ((rc = ensure(h, xt, (size_t)Ns * d * 8)) || (rc = ensure(h, xtsq, (size_t)Ns * 8))) { cleanup(); return rc; }
+    double *d0 = S0, *d1 = S1, *d2 = S2;
+    if (mem == GPX_MEM_HOST) {
+        if ((rc = ensure(h, o0, (size_t)Ns * 8)) || (S1 && (rc = ensure(h, o1, (size_t)Ns * d * 8))) ||
+            (S2 && (rc = ensure(h, o2, (size_t)Ns * d * d * 8)))) { cleanup(); return rc; }
+        d0 = ptr<double>(o0); d1 = S1 ? ptr<double>(o1) : nullptr; d2 = S2 ? ptr<double>(o2) : nullptr;
+    }
+    prep_inputs(h, dXs, Ns, Ns, ptr<double>(xt), ptr<double>(xtsq), st);
+    moments_kernel<<<(int)Ns, 256, moments_smem(d), st>>>(ptr<double>(xt), ptr<double>(xtsq), ptr<double>(h->Xs), ptr<double>(h->xsq),
+                                                          h->N, d, h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), d0, d1, d2);
+    h->launches++;
+    if (mem == GPX_MEM_HOST) {
+        cudaMemcpyAsync(S0, d0, (size_t)Ns * 8, cudaMemcpyDeviceToHost, st);
+        if (S1) cudaMemcpyAsync(S1, d1, (size_t)Ns * d * 8, cudaMemcpyDeviceToHost, st);
+        if (S2) cudaMemcpyAsync(S2, d2, (size_t)Ns * d * d * 8, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) return fail(h, -2, "CUDA error in gpx_predict_moments: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

@@ -4,8 +4,12 @@
 // (K(X*,X), fused with the predictive-mean GEMV partial sums).
 //
 // Arithmetic follows GPy's Stationary._unscaled_dist / _scaled_dist (the library the reference's
-// src/kernels.py:4-7 aliases): inputs divided by the lengthscale(s), r^2 = |a|^2 + |b|^2 - 2 a.b clipped at 0,
-// exact 0 on the diagonal of K(X,X), r = sqrt(r^2), then K_of_r.
+// src/kernels.py:4-7 aliases) OPERATION BY OPERATION:
+//   ARD:        inputs divided by the lengthscales first, r^2 = |a|^2 + |b|^2 - 2 a.b clipped at 0, r = sqrt(r^2);
+//   isotropic:  the same Gram trick on the UNSCALED inputs, then r = sqrt(r^2) / lengthscale
+// (exact 0 on the diagonal of K(X,X)), then K_of_r.  The order matters: with |x / l| ~ 2000 (BASELINE config C4) scaling
+// first moves r^2 by ~1e-9 and the predictive mean by ~7e-7; with GPy's order r^2 reproduces numpy bit for bit at d = 1.
+// |x|^2 is accumulated like numpy's pairwise np.sum(np.square(X), 1) (no FMA contraction, 8 partial sums for d >= 8).
 //
 // Roofline: the K(X,X) build writes 8 B per element once (HBM-write bound: 8*N(N+1)/2 + 8*N*d bytes) but at small
 // d it is bound by the fp64 exp/sqrt ALU work (~60 DFMA-equivalents per element); both rates are reported.
@@ -15,19 +19,75 @@ namespace {
 
 constexpr int kMaxD = 64;
 
-__global__ void scale_x_kernel(const double* __restrict__ X, int64_t N, int64_t Np, int d,
-                               const double* __restrict__ ls, int n_ls, double* __restrict__ Xs,
-                               double* __restrict__ xsq) {
+// numpy's pairwise summation (pairwise_sum_DOUBLE) of the squares of a[0..n): sequential below 8 terms, 8 running sums
+// combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential remainder up to 128 terms, recursive halving above.
+// No FMA contraction (np.square then np.sum).  Verified term by term against numpy for d = 1..300.
+__device__ double gpx_numpy_sumsq(const double* a, int n) {
+    if (n < 8) {
+        double s = -0.0;
+        for (int i = 0; i < n; i++) s = __dadd_rn(s, __dmul_rn(a[i], a[i]));
+        return s;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) r[u] = __dmul_rn(a[u], a[u]);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) r[u] = __dadd_rn(r[u], __dmul_rn(a[i + u], a[i + u]));
+        }
+        double s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                             __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; i++) s = __dadd_rn(s, __dmul_rn(a[i], a[i]));
+        return s;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(gpx_numpy_sumsq(a, n2), gpx_numpy_sumsq(a + n2, n - n2));
+}
+
+// Loader of the inputs (training or test):  v = X[i][k];  fused NormalizerModel z-score v = (v - shift_k) / scale_k
+// (reference src/models/normalizer.py:36-48);  ARD: v /= lengthscale_k.  Rows i >= N are zero padding.
+// xsq[i] = sum_k v^2 in numpy's summation order (np.sum(np.square(X), 1)) so that r^2 matches the reference's rounding.
+__global__ void prep_x_kernel(const double* __restrict__ X, int64_t N, int64_t Np, int d,
+                              const double* __restrict__ ls, int ard, const double* __restrict__ shift,
+                              const double* __restrict__ scale, double* __restrict__ Xs, double* __restrict__ xsq) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Np) return;
-    double s = 0.0;
     for (int k = 0; k < d; k++) {
         double v = 0.0;
-        if (i < N) v = X[i * d + k] / ls[n_ls == 1 ? 0 : k];
+        if (i < N) {
+            v = X[i * d + k];
+            if (shift) v = (v - shift[k]) / scale[k];
+            if (ard) v = v / ls[k];
+        }
         Xs[i * d + k] = v;
-        s += v * v;
     }
-    xsq[i] = s;
+    xsq[i] = gpx_numpy_sumsq(Xs + i * d, d);
+}
+
+// Column statistics for the fused normaliser: stats[k] = mean_k, stats[d + k] = population std_k (np.std, ddof 0) of the
+// (N, d) row-major array A.  One CTA per column, two passes, fixed-order tree reductions (deterministic).
+__global__ void __launch_bounds__(256) col_stats_kernel(const double* __restrict__ A, int64_t N, int d, double* __restrict__ stats) {
+    __shared__ double red[256];
+    __shared__ double s_mean;
+    const int k = blockIdx.x, tid = threadIdx.x;
+    double s = 0.0;
+    for (int64_t i = tid; i < N; i += 256) s += A[i * d + k];
+    red[tid] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
+    if (tid == 0) s_mean = red[0] / (double)N;
+    __syncthreads();
+    const double m = s_mean;
+    s = 0.0;
+    for (int64_t i = tid; i < N; i += 256) { const double v = A[i * d + k] - m; s = fma(v, v, s); }
+    __syncthreads();
+    red[tid] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
+    if (tid == 0) { stats[k] = m; stats[d + k] = sqrt(red[0] / (double)N); }
 }
 
 // One CTA (256 threads) per output tile.  Rows come from (Xa, asq) tile ti, columns from (Xb, bsq) tile tj.
@@ -38,7 +98,7 @@ __device__ __forceinline__ void build_tile(double* __restrict__ out, const doubl
                                            const double* __restrict__ asq, int64_t Na, int ti,
                                            const double* __restrict__ Xb, const double* __restrict__ bsq,
                                            int64_t Nb, int tj, int d, int kernel_id, double variance,
-                                           double diag_add, double* sm, double (*vals)[16][2]) {
+                                           double rdiv, double diag_add, double* sm, double (*vals)[16][2]) {
     // the input dimension is processed in chunks of at most kMaxD columns (any d is supported)
     const int dcap = d < kMaxD ? d : kMaxD;
     const int dp = dcap | 1;
@@ -94,11 +154,11 @@ __device__ __forceinline__ void build_tile(double* __restrict__ out, const doubl
                 double kv;
                 if (kSymmetric) {
                     if (gi == gj) r2 = 0.0;
-                    kv = gpx_k_of_r2(kernel_id, variance, r2);
+                    kv = gpx_k_of_r(kernel_id, variance, gpx_scaled_r(r2, rdiv));
                     if (gi == gj) kv += diag_add;
                     if (gi >= Na || gj >= Nb) kv = (gi == gj) ? 1.0 : 0.0;  // identity padding
                 } else {
-                    kv = gpx_k_of_r2(kernel_id, variance, r2);
+                    kv = gpx_k_of_r(kernel_id, variance, gpx_scaled_r(r2, rdiv));
                     if (gi >= Na || gj >= Nb) kv = 0.0;
                 }
                 v[h] = kv;
@@ -111,15 +171,15 @@ __device__ __forceinline__ void build_tile(double* __restrict__ out, const doubl
 }
 
 // K(X,X) + diag_add I into the packed lower factor storage: grid (nt, number of tile columns handled here).
-__global__ void __launch_bounds__(256) kbuild_lower_kernel(TileMat L, int nt, int jfirst, int jstep,
+__global__ void __launch_bounds__(256) kbuild_lower_kernel(TileMat L, int nt, int jfirst, int jstep, int i_first,
                                                            const double* __restrict__ Xs,
                                                            const double* __restrict__ xsq, int64_t N, int d,
-                                                           int kernel_id, double variance, double diag_add) {
+                                                           int kernel_id, double variance, double rdiv, double diag_add) {
     extern __shared__ __align__(16) double sm[];
     const int J = jfirst + blockIdx.y * jstep;
-    const int I = blockIdx.x;
-    if (J >= nt || I < J) return;
-    build_tile<true>(tile_ptr(L, I, J), Xs, xsq, N, I, Xs, xsq, N, J, d, kernel_id, variance, diag_add, sm, nullptr);
+    const int I = i_first + blockIdx.x;
+    if (J >= nt || I >= nt || I < J) return;
+    build_tile<true>(tile_ptr(L, I, J), Xs, xsq, N, I, Xs, xsq, N, J, d, kernel_id, variance, rdiv, diag_add, sm, nullptr);
 }
 
 // K(X*, X) tiles (rows = test points, cols = training points) into Tt (if Tt.base != null) and the fused
@@ -128,17 +188,31 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(TileMat L, int nt, in
 __global__ void __launch_bounds__(256) kcross_kernel(TileMat Tt, int nbt, int nt, const double* __restrict__ Xt,
                                                      const double* __restrict__ xtsq, int64_t Nt_valid,
                                                      const double* __restrict__ Xs, const double* __restrict__ xsq,
-                                                     int64_t N, int d, int kernel_id, double variance,
+                                                     int64_t N, int d, int kernel_id, double variance, double rdiv,
                                                      const double* __restrict__ alpha, int O, int64_t Np,
-                                                     double* __restrict__ mean_partial) {
+                                                     double* __restrict__ mean_partial, double* __restrict__ vec_out,
+                                                     int vec_rows) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[4][GPX_TILE];  // [t][row]
     const int n = blockIdx.x, J = blockIdx.y;
     double vals[2][16][2];
     double* out = Tt.base ? tile_ptr(Tt, n, J) : nullptr;
-    build_tile<false>(out, Xt, xtsq, Nt_valid, n, Xs, xsq, N, J, d, kernel_id, variance, 0.0, sm, vals);
-    if (!mean_partial) return;
+    build_tile<false>(out, Xt, xtsq, Nt_valid, n, Xs, xsq, N, J, d, kernel_id, variance, rdiv, 0.0, sm, vals);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    if (vec_out) {
+        // latency path (few test points): k(x*_s, X) as right-hand-side vectors vec_out[s][Np] for the GEMV-style solve
+#pragma unroll
+        for (int rb = 0; rb < 2; rb++) {
+            const int r = warp * 16 + rb * 8 + g;
+            if (n == 0 && r < vec_rows) {
+#pragma unroll
+                for (int kc = 0; kc < 16; kc++)
+                    *reinterpret_cast<double2*>(vec_out + (int64_t)r * Np + (int64_t)J * GPX_TILE + kc * 8 + 2 * t) =
+                        make_double2(vals[rb][kc][0], vals[rb][kc][1]);
+            }
+        }
+    }
+    if (!mean_partial) return;
     for (int o = 0; o < O; o++) {
         const double* al = alpha + (int64_t)o * Np + (int64_t)J * GPX_TILE;
 #pragma unroll
@@ -162,20 +236,27 @@ __global__ void __launch_bounds__(256) kcross_kernel(TileMat Tt, int nbt, int nt
 }
 
 // mean[n*128 + r][o] = mean_const + sum_J mean_partial[J][n][r][o]   (fixed summation order: deterministic)
+// Fused output de-normalisation (reference normalizer.py:102-114): mean * std_o + mean_o.
 __global__ void mean_reduce_kernel(const double* __restrict__ mean_partial, int nbt, int nt, int O, double mean_const,
-                                   double* __restrict__ mean, int64_t row0, int64_t Ns) {
+                                   const double* __restrict__ ystats, double* __restrict__ mean, int64_t row0, int64_t Ns) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index over nbt*128*O
     int64_t total = (int64_t)nbt * GPX_TILE * O;
     if (e >= total) return;
     double s = 0.0;
     for (int J = 0; J < nt; J++) s += mean_partial[(int64_t)J * total + e];
     int64_t row = row0 + e / O;
-    if (row < Ns) mean[row * O + (e % O)] = s + mean_const;
+    const int o = (int)(e % O);
+    double m = s + mean_const;
+    if (ystats) m = m * ystats[O + o] + ystats[o];
+    if (row < Ns) mean[row * O + o] = m;
 }
 
 // var[n] = variance + noise - sum_j Tt[n][j]^2 : one CTA per test tile, 256 threads = (row, half of the chunks)
-__global__ void __launch_bounds__(256) var_reduce_kernel(TileMat Tt, int nt, double prior_var, double* __restrict__ var,
-                                                         int64_t row0, int64_t Ns) {
+// var_cols = 1: one shared variance per test row (GPy); var_cols = O: (Ns, O), each column scaled by std_o^2 when the
+// fused output normaliser is on (reference denormalize_variance) or plainly replicated when it is off.
+__global__ void __launch_bounds__(256) var_reduce_kernel(TileMat Tt, int nt, double prior_var,
+                                                         const double* __restrict__ ystats, int var_cols,
+                                                         double* __restrict__ var, int64_t row0, int64_t Ns) {
     __shared__ double red[GPX_TILE];
     const int n = blockIdx.x, tid = threadIdx.x, r = tid & 127, half = tid >> 7;
     double s0 = 0.0, s1 = 0.0;
@@ -197,7 +278,13 @@ __global__ void __launch_bounds__(256) var_reduce_kernel(TileMat Tt, int nt, dou
     if (half == 0) {
         s += red[r];
         int64_t row = row0 + (int64_t)n * GPX_TILE + r;
-        if (row < Ns) var[row] = prior_var - s;
+        if (row < Ns) {
+            const double v = prior_var - s;
+            for (int o = 0; o < var_cols; o++) {
+                const double sd = ystats ? ystats[var_cols + o] : 1.0;   // ystats = [O means | O stds]; var_cols == O here
+                var[row * var_cols + o] = ystats ? v * (sd * sd) : v;
+            }
+        }
     }
 }
 
@@ -224,48 +311,66 @@ static size_t kb_smem(int d) {
 int gpx_kbuild_max_d() { return 1 << 20; }   // any input dimension (processed in chunks of kMaxD)
 int gpx_grad_max_d() { return kMaxD; }       // the gradient kernel keeps one partial sum per lengthscale in registers
 
+static void gpx_grad_init_attr();   // defined after the gradient kernel below
+
+// per device (function attributes are per device): called from gpx_create after cudaSetDevice
 void gpx_kbuild_init() {
+    gpx_grad_init_attr();
     size_t s = kb_smem(kMaxD);
     cudaFuncSetAttribute(kbuild_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s);
     cudaFuncSetAttribute(kcross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s);
 }
 
-void gpx_launch_scale_x(const double* X, int64_t N, int64_t Np, int d, const double* ls, int n_ls, double* Xs,
-                        double* xsq, cudaStream_t st) {
-    int threads = 256;
+void gpx_launch_prep_x(const double* X, int64_t N, int64_t Np, int d, const double* ls, int ard, const double* shift,
+                       const double* scale, double* Xs, double* xsq, cudaStream_t st) {
+    int threads = 128;
     int blocks = (int)((Np + threads - 1) / threads);
-    scale_x_kernel<<<blocks, threads, 0, st>>>(X, N, Np, d, ls, n_ls, Xs, xsq);
+    prep_x_kernel<<<blocks, threads, 0, st>>>(X, N, Np, d, ls, ard, shift, scale, Xs, xsq);
+}
+
+void gpx_launch_col_stats(const double* A, int64_t N, int d, double* stats, cudaStream_t st) {
+    col_stats_kernel<<<d, 256, 0, st>>>(A, N, d, stats);
 }
 
 void gpx_launch_kbuild_lower(TileMat L, int nt, int jfirst, int jstep, int ncols, const double* Xs,
-                             const double* xsq, int64_t N, int d, int kernel_id, double variance, double diag_add,
-                             cudaStream_t st) {
+                             const double* xsq, int64_t N, int d, int kernel_id, double variance, double rdiv,
+                             double diag_add, cudaStream_t st) {
     if (ncols <= 0) return;
     dim3 grid(nt, ncols);
-    kbuild_lower_kernel<<<grid, 256, kb_smem(d), st>>>(L, nt, jfirst, jstep, Xs, xsq, N, d, kernel_id, variance,
+    kbuild_lower_kernel<<<grid, 256, kb_smem(d), st>>>(L, nt, jfirst, jstep, 0, Xs, xsq, N, d, kernel_id, variance, rdiv,
+                                                       diag_add);
+}
+
+// the tile rows [i_first, nt) of K(X,X) + diag_add I only (gpx_append: rows of new observations)
+void gpx_launch_kbuild_rows(TileMat L, int nt, int i_first, const double* Xs, const double* xsq, int64_t N, int d,
+                            int kernel_id, double variance, double rdiv, double diag_add, cudaStream_t st) {
+    if (i_first >= nt) return;
+    dim3 grid(nt - i_first, nt);
+    kbuild_lower_kernel<<<grid, 256, kb_smem(d), st>>>(L, nt, 0, 1, i_first, Xs, xsq, N, d, kernel_id, variance, rdiv,
                                                        diag_add);
 }
 
 void gpx_launch_kcross(TileMat Tt, int nb, int nbt_layout, int nt, const double* Xt, const double* xtsq,
                        int64_t Nt_valid, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
-                       double variance, const double* alpha, int O, int64_t Np, double* mean_partial, cudaStream_t st) {
+                       double variance, double rdiv, const double* alpha, int O, int64_t Np, double* mean_partial,
+                       cudaStream_t st, double* vec_out, int vec_rows) {
     dim3 grid(nb, nt);
     kcross_kernel<<<grid, 256, kb_smem(d), st>>>(Tt, nbt_layout, nt, Xt, xtsq, Nt_valid, Xs, xsq, N, d, kernel_id, variance,
-                                                 alpha, O, Np, mean_partial);
+                                                 rdiv, alpha, O, Np, mean_partial, vec_out, vec_rows);
 }
 
-void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, double mean_const, double* mean,
-                            int64_t row0, int64_t Ns, cudaStream_t st) {
+void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, double mean_const, const double* ystats,
+                            double* mean, int64_t row0, int64_t Ns, cudaStream_t st) {
     // nbt = layout stride (test tiles per tile column of mean_partial); rows past Ns are skipped in the kernel
     int64_t total = (int64_t)nbt * GPX_TILE * O;
     int threads = 128;
     mean_reduce_kernel<<<(int)((total + threads - 1) / threads), threads, 0, st>>>(mean_partial, nbt, nt, O,
-                                                                                  mean_const, mean, row0, Ns);
+                                                                                  mean_const, ystats, mean, row0, Ns);
 }
 
-void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, double prior_var, double* var, int64_t row0, int64_t Ns,
-                           cudaStream_t st) {
-    var_reduce_kernel<<<nbt, 256, 0, st>>>(Tt, nt, prior_var, var, row0, Ns);
+void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, double prior_var, const double* ystats, int var_cols, double* var,
+                           int64_t row0, int64_t Ns, cudaStream_t st) {
+    var_reduce_kernel<<<nbt, 256, 0, st>>>(Tt, nt, prior_var, ystats, var_cols, var, row0, Ns);
 }
 
 void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double* out, cudaStream_t st) {
@@ -287,8 +392,7 @@ void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double*
 // =====================================================================================================================
 namespace {
 
-__device__ __forceinline__ void gpx_k_and_f(int kernel_id, double variance, double r2, double& k, double& f) {
-    const double r = sqrt(r2);
+__device__ __forceinline__ void gpx_k_and_f(int kernel_id, double variance, double r, double& k, double& f) {
     if (kernel_id == 0) { k = variance * exp(-0.5 * (r * r)); f = k; }
     else if (kernel_id == 1) {
         const double s5 = 2.23606797749978969641;
@@ -311,8 +415,9 @@ constexpr int kMaxGradLs = kMaxD;
 // grid (nt, nt); partial[(I * nt + J) * stride + {0: variance, 1: noise, 2..: lengthscales}]
 __global__ void __launch_bounds__(256) lml_grad_tile_kernel(TileMat Kinv, int nt, const double* __restrict__ Xs,
                                                             const double* __restrict__ xsq, int64_t N, int d,
-                                                            int kernel_id, double variance, const double* __restrict__ ls,
-                                                            int n_ls, const double* __restrict__ alpha, int O, int64_t Np,
+                                                            int kernel_id, double variance, double rdiv,
+                                                            const double* __restrict__ ls, int n_ls,
+                                                            const double* __restrict__ alpha, int O, int64_t Np,
                                                             double* __restrict__ partial, int stride) {
     extern __shared__ __align__(16) double sm[];
     const int I = blockIdx.x, J = blockIdx.y;
@@ -355,7 +460,7 @@ __global__ void __launch_bounds__(256) lml_grad_tile_kernel(TileMat Kinv, int nt
                 double r2 = fmax(-2.0 * dot + (sasq[r] + sbsq[c]), 0.0);
                 if (gi == gj) r2 = 0.0;
                 double kv, f;
-                gpx_k_and_f(kernel_id, variance, r2, kv, f);
+                gpx_k_and_f(kernel_id, variance, gpx_scaled_r(r2, rdiv), kv, f);
                 double aa = 0.0;
                 for (int o = 0; o < O; o++) aa = fma(alpha[(int64_t)o * Np + gi], alpha[(int64_t)o * Np + gj], aa);
                 const double kinv = hh ? kinv2.y : kinv2.x;
@@ -366,7 +471,7 @@ __global__ void __launch_bounds__(256) lml_grad_tile_kernel(TileMat Kinv, int nt
                 if (n_ls == 1) {
                     double s = 0.0;
                     for (int k = 0; k < d; k++) { double dx = sa[r * dp + k] - sb[c * dp + k]; s = fma(dx, dx, s); }
-                    gls[0] = fma(wf, s, gls[0]);
+                    gls[0] = fma(wf, s / (rdiv * rdiv), gls[0]);   // isotropic: the staged inputs are unscaled
                 } else {
                     for (int k = 0; k < d; k++) { double dx = sa[r * dp + k] - sb[c * dp + k]; gls[k] = fma(wf, dx * dx, gls[k]); }
                 }
@@ -435,24 +540,23 @@ __global__ void sum_kernel(const double* __restrict__ a, int64_t n, double* __re
 
 }  // namespace
 
+static void gpx_grad_init_attr() {
+    cudaFuncSetAttribute(lml_grad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((2 * GPX_TILE * (kMaxD | 1) + 2 * GPX_TILE + 8 * (2 + kMaxD)) * sizeof(double)));
+}
+
 void gpx_launch_identity_tiles(TileMat T, int nt, cudaStream_t st) {
     dim3 grid(nt, nt);
     identity_tiles_kernel<<<grid, 256, 0, st>>>(T, nt);
 }
 
 void gpx_launch_lml_grad(TileMat Kinv, int nt, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
-                         double variance, const double* ls, int n_ls, const double* alpha, int O, int64_t Np,
+                         double variance, double rdiv, const double* ls, int n_ls, const double* alpha, int O, int64_t Np,
                          double* partial, double* out, cudaStream_t st) {
     const int stride = 2 + n_ls;
     size_t smem = (size_t)(2 * GPX_TILE * (d | 1) + 2 * GPX_TILE + 8 * stride) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lml_grad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)((2 * GPX_TILE * (kMaxD | 1) + 2 * GPX_TILE + 8 * (2 + kMaxD)) * sizeof(double)));
-        attr = true;
-    }
     dim3 grid(nt, nt);
-    lml_grad_tile_kernel<<<grid, 256, smem, st>>>(Kinv, nt, Xs, xsq, N, d, kernel_id, variance, ls, n_ls, alpha, O, Np,
+    lml_grad_tile_kernel<<<grid, 256, smem, st>>>(Kinv, nt, Xs, xsq, N, d, kernel_id, variance, rdiv, ls, n_ls, alpha, O, Np,
                                                   partial, stride);
     lml_grad_reduce_kernel<<<stride, 256, 0, st>>>(partial, nt, stride, stride, out);
     // out[stride] = sum(alpha): gradient of the constant mean

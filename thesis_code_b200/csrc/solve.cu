@@ -126,12 +126,13 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(TileMat L, const double* 
 
 // logdet = 2 sum_i log L_ii = -2 sum_i log (Linv_ii)  (read from the inverted diagonal tiles, which every rank holds);
 // quad = sum alpha * resid.  One CTA, fixed order.
+// n_rows = nt * 128 rows have a diagonal tile; Np >= n_rows is the padded vector length (zeros beyond N).
 __global__ void __launch_bounds__(1024) lml_kernel(const double* __restrict__ linv, const double* __restrict__ alpha,
-                                                   const double* __restrict__ resid, int64_t Np, int O,
+                                                   const double* __restrict__ resid, int64_t n_rows, int64_t Np, int O,
                                                    double* __restrict__ out2) {
     __shared__ double red[2][32];
     double ld = 0.0, q = 0.0;
-    for (int64_t i = threadIdx.x; i < Np; i += blockDim.x) {
+    for (int64_t i = threadIdx.x; i < n_rows; i += blockDim.x) {
         int J = (int)(i >> 7), r = (int)(i & 127);
         ld -= log(linv[(int64_t)J * GPX_TILE_ELEMS + gpx_tile_idx(r, r)]);
     }
@@ -150,13 +151,20 @@ __global__ void __launch_bounds__(1024) lml_kernel(const double* __restrict__ li
     }
 }
 
-// resid[o][i] = (i < N) ? Y[i][o] - mean_const : 0  (transposes the caller's (N, O) row-major Y)
+// resid[o][i] = (i < N) ? Y'[i][o] - mean_const : 0  (transposes the caller's (N, O) row-major Y);
+// Y' = (Y - mean_o) / std_o when the fused output normaliser is on (ystats = [O means | O stds]), else Y.
 __global__ void resid_kernel(const double* __restrict__ Y, int64_t N, int64_t Np, int O, double mean_const,
-                             double* __restrict__ resid) {
+                             const double* __restrict__ ystats, double* __restrict__ resid) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= Np * O) return;
     int64_t o = e / Np, i = e - o * Np;
-    resid[e] = (i < N) ? Y[i * O + o] - mean_const : 0.0;
+    double v = 0.0;
+    if (i < N) {
+        v = Y[i * O + o];
+        if (ystats) v = (v - ystats[o]) / ystats[O + o];
+        v -= mean_const;
+    }
+    resid[e] = v;
 }
 
 // out[i][o] = in[o][i] for i < N
@@ -182,14 +190,15 @@ void gpx_launch_bwd_step(TileMat L, const double* linv, int I, double* z, double
     bwd_step_kernel<<<grid, 256, 0, st>>>(L, linv, I, z, a, Np, O, compute_alpha, ncols, jbase, jW, jstride);
 }
 
-void gpx_launch_lml(const double* linv, const double* alpha, const double* resid, int64_t Np, int O, double* out2,
-                    cudaStream_t st) {
-    lml_kernel<<<1, 1024, 0, st>>>(linv, alpha, resid, Np, O, out2);
+void gpx_launch_lml(const double* linv, const double* alpha, const double* resid, int64_t n_rows, int64_t Np, int O,
+                    double* out2, cudaStream_t st) {
+    lml_kernel<<<1, 1024, 0, st>>>(linv, alpha, resid, n_rows, Np, O, out2);
 }
 
-void gpx_launch_resid(const double* Y, int64_t N, int64_t Np, int O, double mean_const, double* resid, cudaStream_t st) {
+void gpx_launch_resid(const double* Y, int64_t N, int64_t Np, int O, double mean_const, const double* ystats, double* resid,
+                      cudaStream_t st) {
     int64_t total = Np * O;
-    resid_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(Y, N, Np, O, mean_const, resid);
+    resid_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(Y, N, Np, O, mean_const, ystats, resid);
 }
 
 void gpx_launch_untranspose(const double* in, int64_t N, int64_t Np, int O, double* out, cudaStream_t st) {

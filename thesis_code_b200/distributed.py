@@ -73,3 +73,32 @@ def init_handle_comm(handle, dist, rank=None, world=None):
     dist.broadcast(t, src=0)
     uid = bytes(t.cpu().numpy().astype(np.uint8).tolist())
     handle.comm_init(rank, world, uid)
+
+
+def problem_fingerprint(X, Y, theta):
+    """Six numbers that must agree on every rank of a sharded fit: shapes and CRC32s of the data and the parameters."""
+    import zlib
+
+    def crc(a):
+        return float(zlib.crc32(np.ascontiguousarray(a, dtype=np.float64).view(np.uint8).ravel()))
+    return np.array([X.shape[0], X.shape[1], Y.shape[1], crc(X), crc(Y), crc(theta)], dtype=np.float64)
+
+
+def check_same_problem(handle, X, Y, theta, dist=None):
+    """A sharded fit is a collective: every rank must pass the same X, Y and hyper-parameters, otherwise panels of
+    different problems get mixed (or the ranks hang).  One small all-reduce (max of [f, -f]) compares the fingerprints."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    fp = problem_fingerprint(X, Y, theta)
+    device = torch.device("cuda", handle.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(np.concatenate([fp, -fp])).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.cpu().numpy()
+    if not np.array_equal(t[:fp.size], -t[fp.size:]):
+        from ._gpx import GpxError
+        raise GpxError("sharded GPModel: the ranks were given different data or hyper-parameters "
+                       "(N, d, O, crc(X), crc(Y), crc(theta) max {} vs min {}); a sharded fit is a collective over "
+                       "identical inputs -- use model.distributed = False for per-rank models".format(t[:fp.size], -t[fp.size:]))
