@@ -51,6 +51,7 @@ NcclApi& nccl() {
 void gemm(gpx_t* h, const GemmJob& job_in, cudaStream_t st) {
     GemmJob job = job_in;
     job.chunk = h->gemm_max_chunk > 0 ? h->gemm_max_chunk : (h->world > 1 ? 4 : 16);
+    job.strip = h->gemm_strip;
     // Only launches on the main (update) stream are timed and counted: the panel-factorisation GEMMs of stream F
     // overlap them, so adding their durations would count the same wall time twice.
     if (!h->gemm_timing || st != h->st) {
@@ -364,7 +365,7 @@ void gpx_destroy(gpx_t* h) {
     DevBuf* all[] = {&h->Xs, &h->xsq, &h->ls, &h->L, &h->linv, &h->coloff, &h->vcoloff, &h->linv_coloff, &h->resid,
                      &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->gbuf[0], &h->gbuf[1], &h->cache,
                      &h->ucoloff, &h->Tt,
-                     &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar, &h->sp, &h->xstats, &h->ystats};
+                     &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar, &h->sp, &h->xstats, &h->ystats, &h->var_partial};
     for (DevBuf* b : all) release(h, *b);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->pin) cudaFreeHost(h->pin);
@@ -430,6 +431,7 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "nccl_lo_ctas")) { h->nccl_lo_ctas = (int)value; return 0; }  // takes effect at gpx_comm_init
     if (!strcmp(name, "trace")) { h->trace = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_max_chunk")) { h->gemm_max_chunk = (int)value; return 0; }
+    if (!strcmp(name, "gemm_strip")) { if (value < 0 || value > 64) return fail(h, -1, "gemm_strip out of range"); h->gemm_strip = (int)value; return 0; }
     if (!strcmp(name, "reserve_rows")) { if (value < 0) return fail(h, -1, "bad reserve_rows"); h->reserve_rows = value; return 0; }
     if (!strcmp(name, "predict_graph")) { h->predict_graph = value ? 1 : 0; h->gen++; return 0; }
     return fail(h, -1, "unknown option %s", name);
@@ -544,7 +546,10 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
             size_t fr = 0, tot = 0;
             GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
             fr += h->cache.bytes;   // reusable
-            double reserve = 0.35 * (double)fr > 16e9 ? 0.35 * (double)fr : 16e9;   // predict workspaces, NCCL, the caller
+            // reserve for the predict workspaces (their batch size adapts to what is left), NCCL and the caller.  Round 1 kept
+            // 35 % free, which left 10-30 % of L to be re-broadcast in every predict sweep at N = 200k; 10 % (>= 8 GB) lets every
+            // rank keep a full replica of the factor there (160 GB of the 180 GB), so the sweep runs without any exchange.
+            double reserve = 0.10 * (double)fr > 8e9 ? 0.10 * (double)fr : 8e9;
             budget = (double)fr > reserve ? (double)fr - reserve : 0.0;
             if (h->cache_limit_mb > 0 && budget > 1e6 * (double)h->cache_limit_mb) budget = 1e6 * (double)h->cache_limit_mb;
         }
@@ -872,8 +877,7 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
             phase_end(h, GPX_PHASE_PREDICT_TRSM);
             phase_begin(h, GPX_PHASE_PREDICT_REDUCE);
             if (nb > 0) {
-                gpx_launch_var_reduce(Tt, nb, nt, prior_var, y_stats(h), var_cols, dvar, row0, row0 + valid, h->st);
-                h->launches++;
+                if ((rc = var_reduce(h, Tt, nb, prior_var, var_cols, dvar, row0, row0 + valid))) return rc;
             }
             phase_end(h, GPX_PHASE_PREDICT_REDUCE);
         }
@@ -1073,7 +1077,7 @@ double gpx_debug_gemm(gpx_t* h, int rows, int cols, int ktiles, int overwrite, i
     g.B = TileMat{ptr<double>(B), ptr<int64_t>(offB), 0};
     g.C = TileMat{ptr<double>(C), ptr<int64_t>(offC), 0};
     g.tri = 0; g.i0 = 0; g.i1 = rows; g.ncols = cols; g.jbase = 0; g.jW = GPX_JW_CONTIG; g.jstride = 0;
-    g.k0 = 0; g.k1 = ktiles; g.bdiag = 0; g.overwrite = overwrite; g.chunk = max_chunk;
+    g.k0 = 0; g.k1 = ktiles; g.bdiag = 0; g.overwrite = overwrite; g.chunk = max_chunk; g.strip = h->gemm_strip;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     gpx_launch_gemm(g, h->num_sms, h->st, nullptr);

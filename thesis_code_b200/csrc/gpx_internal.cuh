@@ -23,8 +23,9 @@ void gpx_launch_kbuild_lower(TileMat L, int nt, int jfirst, int jstep, int ncols
 // ystats: null, or [O means | O stds] of the fused output normaliser (mean -> mean * std + mean_y, var -> var * std^2)
 void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, double mean_const, const double* ystats,
                             double* mean, int64_t row0, int64_t Ns, cudaStream_t st);
-void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, double prior_var, const double* ystats, int var_cols, double* var,
-                           int64_t row0, int64_t Ns, cudaStream_t st);
+int gpx_var_reduce_splits(int nbt, int nt, int num_sms);
+void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, int S, double* partial, double prior_var, const double* ystats,
+                           int var_cols, double* var, int64_t row0, int64_t Ns, cudaStream_t st);
 void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double* out, cudaStream_t st);
 void gpx_launch_fwd_step(TileMat L, const double* linv, int nt, int J, double* b, double* z, int64_t Np, int O,
                          int max_ctas, cudaStream_t st);
@@ -90,6 +91,7 @@ struct gpx_handle {
     int lookahead = 1;
     int gemm_max_chunk = 0;               // 0 = auto: 16 on one GPU, 4 when sharded (shorter CTAs let the panel
                                           // factorisation and NCCL kernels of the other streams in sooner)
+    int gemm_strip = 0;                   // option "gemm_strip": rasterisation strip width of the tile GEMM (0 = default)
     int trace = 0;                        // 1: per-panel timeline events during the Cholesky (gpx_trace)
     std::vector<cudaEvent_t> tev;         // 6 per panel + 1 base, timing enabled
     std::vector<float> trace_ms;          // 6 per panel: factor start, factor end, panel ready, (a) end, fwd end, (b) end
@@ -139,7 +141,7 @@ struct gpx_handle {
     std::vector<cudaEvent_t> pev;       // per-panel events (3 per panel), no timing
 
     // predict workspaces
-    DevBuf Tt, tt_coloff, Xt, xtsq, mean_partial, dmean, dvar;
+    DevBuf Tt, tt_coloff, Xt, xtsq, mean_partial, dmean, dvar, var_partial;
     // latency path (gpx_predict with <= 128 rows, gpx_update.cu): one persistent workspace, a pinned staging buffer and
     // the captured launch chains
     DevBuf sp;
@@ -251,6 +253,16 @@ inline int wait_for_caller(gpx_t* h) {
 
 void gemm(gpx_t* h, const GemmJob& job_in, cudaStream_t st);
 void gemm_collect(gpx_t* h);
+
+// var = prior - rowsumsq(Tt) for nb test tiles (two launches; the partial-sum buffer is kept in the handle)
+inline int var_reduce(gpx_t* h, TileMat Tt, int nb, double prior_var, int var_cols, double* var, int64_t row0, int64_t Ns) {
+    const int S = gpx_var_reduce_splits(nb, h->nt, h->num_sms);
+    int rc = ensure(h, h->var_partial, (size_t)nb * S * GPX_TILE * 8);
+    if (rc) return rc;
+    gpx_launch_var_reduce(Tt, nb, h->nt, S, ptr<double>(h->var_partial), prior_var, y_stats(h), var_cols, var, row0, Ns, h->st);
+    h->launches += 2;
+    return 0;
+}
 
 // ---- distribution helpers ---------------------------------------------------------------------------------------
 inline int panel_begin(const gpx_t* h, int p) { return p * h->W; }

@@ -361,8 +361,7 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
         gpx_launch_mean_reduce(w.mean_partial, 1, nt, O, h->mean_const, y_stats(h), w.mean, 0, Ns, st);
         h->launches += 3;
         if ((rc = var_trsm(h, Tt, 1))) return rc;
-        gpx_launch_var_reduce(Tt, 1, nt, h->variance + (include_noise ? h->noise : 0.0), y_stats(h), var_cols, w.var, 0, Ns, st);
-        h->launches++;
+        if ((rc = var_reduce(h, Tt, 1, h->variance + (include_noise ? h->noise : 0.0), var_cols, w.var, 0, Ns))) return rc;
     }
     const size_t mb = (size_t)Ns * O * 8, vb = want_var ? (size_t)Ns * var_cols * 8 : 0;
     if (mem == GPX_MEM_HOST) {

@@ -17,7 +17,11 @@
 
 namespace {
 
+#ifndef GPX_KBUILD_MINBLOCKS
+#define GPX_KBUILD_MINBLOCKS 2
+#endif
 constexpr int kMaxD = 64;
+constexpr int kMaxFusedO = 4;   // outputs whose mean partial sums are fused into one K*-tile pass (more outputs: more passes)
 
 // numpy's pairwise summation (pairwise_sum_DOUBLE) of the squares of a[0..n): sequential below 8 terms, 8 running sums
 // combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential remainder up to 128 terms, recursive halving above.
@@ -93,12 +97,15 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const double* __restrict
 // One CTA (256 threads) per output tile.  Rows come from (Xa, asq) tile ti, columns from (Xb, bsq) tile tj.
 // Thread mapping = the DMMA accumulator fragment pattern: lane (g = lane>>2, t = lane&3) of warp w owns, for each
 // of its 2 row blocks and 16 column chunks, the pair (r, c..c+1) -> one 16 B store; a warp stores 512 contiguous B.
-template <bool kSymmetric>
+template <bool kSymmetric, bool kFused>
 __device__ __forceinline__ void build_tile(double* __restrict__ out, const double* __restrict__ Xa,
                                            const double* __restrict__ asq, int64_t Na, int ti,
                                            const double* __restrict__ Xb, const double* __restrict__ bsq,
                                            int64_t Nb, int tj, int d, int kernel_id, double variance,
-                                           double rdiv, double diag_add, double* sm, double (*vals)[16][2]) {
+                                           double rdiv, double diag_add, double* sm,
+                                           const double* __restrict__ alpha_tile, int O, int64_t alpha_stride,
+                                           double* __restrict__ red, double* __restrict__ vec_row0, int64_t vec_stride,
+                                           int vec_rows) {
     // the input dimension is processed in chunks of at most kMaxD columns (any d is supported)
     const int dcap = d < kMaxD ? d : kMaxD;
     const int dp = dcap | 1;
@@ -142,6 +149,9 @@ __device__ __forceinline__ void build_tile(double* __restrict__ out, const doubl
             }
         }
         const double ra = sasq[r];
+        double msum[kMaxFusedO];
+#pragma unroll
+        for (int o = 0; o < kMaxFusedO; o++) msum[o] = 0.0;
 #pragma unroll
         for (int kc = 0; kc < 16; kc++) {
             double v[2];
@@ -163,15 +173,26 @@ __device__ __forceinline__ void build_tile(double* __restrict__ out, const doubl
                 }
                 v[h] = kv;
             }
-            if (vals) { vals[rb][kc][0] = v[0]; vals[rb][kc][1] = v[1]; }
             if (out) *reinterpret_cast<double2*>(out + kc * 1024 + r * 8 + 2 * t) = make_double2(v[0], v[1]);
+            if (kFused && vec_row0 && r < vec_rows)   // latency path: k(x*_r, X) as right-hand-side vectors for the GEMV-style solve
+                *reinterpret_cast<double2*>(vec_row0 + (int64_t)r * vec_stride + kc * 8 + 2 * t) = make_double2(v[0], v[1]);
+            if (kFused && alpha_tile) {               // fused predictive-mean partial sums: sum_c K[r][c] alpha[o][c] over this thread's columns
+                const int c = kc * 8 + 2 * t;
+                for (int o = 0; o < O && o < kMaxFusedO; o++) {
+                    const double* al = alpha_tile + (int64_t)o * alpha_stride;
+                    msum[o] = fma(v[0], al[c], msum[o]);
+                    msum[o] = fma(v[1], al[c + 1], msum[o]);
+                }
+            }
         }
+        if (kFused && alpha_tile)
+            for (int o = 0; o < O && o < kMaxFusedO; o++) red[(o * 4 + t) * GPX_TILE + r] = msum[o];
     }
     if (out) gpx_publish_for_async_proxy();
 }
 
 // K(X,X) + diag_add I into the packed lower factor storage: grid (nt, number of tile columns handled here).
-__global__ void __launch_bounds__(256) kbuild_lower_kernel(TileMat L, int nt, int jfirst, int jstep, int i_first,
+__global__ void __launch_bounds__(256, GPX_KBUILD_MINBLOCKS) kbuild_lower_kernel(TileMat L, int nt, int jfirst, int jstep, int i_first,
                                                            const double* __restrict__ Xs,
                                                            const double* __restrict__ xsq, int64_t N, int d,
                                                            int kernel_id, double variance, double rdiv, double diag_add) {
@@ -179,13 +200,14 @@ __global__ void __launch_bounds__(256) kbuild_lower_kernel(TileMat L, int nt, in
     const int J = jfirst + blockIdx.y * jstep;
     const int I = i_first + blockIdx.x;
     if (J >= nt || I >= nt || I < J) return;
-    build_tile<true>(tile_ptr(L, I, J), Xs, xsq, N, I, Xs, xsq, N, J, d, kernel_id, variance, rdiv, diag_add, sm, nullptr);
+    build_tile<true, false>(tile_ptr(L, I, J), Xs, xsq, N, I, Xs, xsq, N, J, d, kernel_id, variance, rdiv, diag_add, sm, nullptr, 0, 0,
+                     nullptr, nullptr, 0, 0);
 }
 
 // K(X*, X) tiles (rows = test points, cols = training points) into Tt (if Tt.base != null) and the fused
 // predictive-mean partial sums  mean_partial[J][n][o] = sum_{j in tile J} K(x*_n, x_j) alpha[o][j].
 // grid (nbt, nt).
-__global__ void __launch_bounds__(256) kcross_kernel(TileMat Tt, int nbt, int nt, const double* __restrict__ Xt,
+__global__ void __launch_bounds__(256, 2) kcross_kernel(TileMat Tt, int nbt, int nt, const double* __restrict__ Xt,
                                                      const double* __restrict__ xtsq, int64_t Nt_valid,
                                                      const double* __restrict__ Xs, const double* __restrict__ xsq,
                                                      int64_t N, int d, int kernel_id, double variance, double rdiv,
@@ -193,45 +215,27 @@ __global__ void __launch_bounds__(256) kcross_kernel(TileMat Tt, int nbt, int nt
                                                      double* __restrict__ mean_partial, double* __restrict__ vec_out,
                                                      int vec_rows) {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double red[4][GPX_TILE];  // [t][row]
+    __shared__ double red[kMaxFusedO * 4 * GPX_TILE];  // [o][t][row]
     const int n = blockIdx.x, J = blockIdx.y;
-    double vals[2][16][2];
+    const int tid = threadIdx.x;
     double* out = Tt.base ? tile_ptr(Tt, n, J) : nullptr;
-    build_tile<false>(out, Xt, xtsq, Nt_valid, n, Xs, xsq, N, J, d, kernel_id, variance, rdiv, 0.0, sm, vals);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    if (vec_out) {
-        // latency path (few test points): k(x*_s, X) as right-hand-side vectors vec_out[s][Np] for the GEMV-style solve
-#pragma unroll
-        for (int rb = 0; rb < 2; rb++) {
-            const int r = warp * 16 + rb * 8 + g;
-            if (n == 0 && r < vec_rows) {
-#pragma unroll
-                for (int kc = 0; kc < 16; kc++)
-                    *reinterpret_cast<double2*>(vec_out + (int64_t)r * Np + (int64_t)J * GPX_TILE + kc * 8 + 2 * t) =
-                        make_double2(vals[rb][kc][0], vals[rb][kc][1]);
-            }
-        }
-    }
-    if (!mean_partial) return;
-    for (int o = 0; o < O; o++) {
-        const double* al = alpha + (int64_t)o * Np + (int64_t)J * GPX_TILE;
-#pragma unroll
-        for (int rb = 0; rb < 2; rb++) {
-            double s = 0.0;
-#pragma unroll
-            for (int kc = 0; kc < 16; kc++) {
-                int c = kc * 8 + 2 * t;
-                s = fma(vals[rb][kc][0], al[c], s);
-                s = fma(vals[rb][kc][1], al[c + 1], s);
-            }
-            red[t][warp * 16 + rb * 8 + g] = s;
-        }
+    // The mean partial sums are accumulated inside the tile builder's epilogue (no per-thread copy of the tile: 239 -> ~128
+    // registers, two CTAs per SM).  Outputs are handled kMaxFusedO at a time; passes after the first only recompute the sums.
+    for (int o0 = 0; o0 < (mean_partial ? O : 1); o0 += kMaxFusedO) {
+        const int Oc = mean_partial ? ((O - o0 < kMaxFusedO) ? (O - o0) : kMaxFusedO) : 0;
+        const bool first = (o0 == 0);
+        if (!first) __syncthreads();
+        build_tile<false, true>(first ? out : nullptr, Xt, xtsq, Nt_valid, n, Xs, xsq, N, J, d, kernel_id, variance, rdiv, 0.0, sm,
+                          mean_partial ? alpha + (int64_t)o0 * Np + (int64_t)J * GPX_TILE : nullptr, Oc, Np, red,
+                          (first && vec_out && n == 0) ? vec_out + (int64_t)J * GPX_TILE : nullptr, Np, vec_rows);
+        if (!mean_partial) return;
         __syncthreads();
-        if (tid < GPX_TILE) {
-            double s = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-            mean_partial[((int64_t)J * nbt + n) * GPX_TILE * O + (int64_t)tid * O + o] = s;
+        for (int e = tid; e < GPX_TILE * Oc; e += blockDim.x) {
+            const int o = e / GPX_TILE, r = e - o * GPX_TILE;
+            const double* rr = red + (o * 4) * GPX_TILE + r;
+            const double s = (rr[0] + rr[GPX_TILE]) + (rr[2 * GPX_TILE] + rr[3 * GPX_TILE]);
+            mean_partial[((int64_t)J * nbt + n) * GPX_TILE * O + (int64_t)r * O + o0 + o] = s;
         }
-        __syncthreads();
     }
 }
 
@@ -252,15 +256,15 @@ __global__ void mean_reduce_kernel(const double* __restrict__ mean_partial, int 
 }
 
 // var[n] = variance + noise - sum_j Tt[n][j]^2 : one CTA per test tile, 256 threads = (row, half of the chunks)
-// var_cols = 1: one shared variance per test row (GPy); var_cols = O: (Ns, O), each column scaled by std_o^2 when the
-// fused output normaliser is on (reference denormalize_variance) or plainly replicated when it is off.
-__global__ void __launch_bounds__(256) var_reduce_kernel(TileMat Tt, int nt, double prior_var,
-                                                         const double* __restrict__ ystats, int var_cols,
-                                                         double* __restrict__ var, int64_t row0, int64_t Ns) {
+// Row sums of squares of Tt, phase 1: grid (nb, S); CTA (n, s) covers the tile columns [s nt / S, (s+1) nt / S) of test
+// tile n and writes 128 partial sums.  S is chosen so that nb * S CTAs fill the GPU (one CTA per test tile left most SMs
+// idle: 650 GB/s at 20 test tiles, profiles/r02_hbm_kernels_ncu_summary.txt).
+__global__ void __launch_bounds__(256) var_partial_kernel(TileMat Tt, int nt, int S, double* __restrict__ partial) {
     __shared__ double red[GPX_TILE];
-    const int n = blockIdx.x, tid = threadIdx.x, r = tid & 127, half = tid >> 7;
+    const int n = blockIdx.x, sidx = blockIdx.y, tid = threadIdx.x, r = tid & 127, half = tid >> 7;
+    const int J0 = (int)((long long)nt * sidx / S), J1 = (int)((long long)nt * (sidx + 1) / S);
     double s0 = 0.0, s1 = 0.0;
-    for (int J = 0; J < nt; J++) {
+    for (int J = J0; J < J1; J++) {
         const double* tp = tile_ptr(Tt, n, J);
 #pragma unroll
         for (int kc = 0; kc < 8; kc++) {
@@ -275,15 +279,26 @@ __global__ void __launch_bounds__(256) var_reduce_kernel(TileMat Tt, int nt, dou
     double s = s0 + s1;
     if (half == 1) red[r] = s;
     __syncthreads();
-    if (half == 0) {
-        s += red[r];
-        int64_t row = row0 + (int64_t)n * GPX_TILE + r;
-        if (row < Ns) {
-            const double v = prior_var - s;
-            for (int o = 0; o < var_cols; o++) {
-                const double sd = ystats ? ystats[var_cols + o] : 1.0;   // ystats = [O means | O stds]; var_cols == O here
-                var[row * var_cols + o] = ystats ? v * (sd * sd) : v;
-            }
+    if (half == 0) partial[((int64_t)n * S + sidx) * GPX_TILE + r] = s + red[r];
+}
+
+// phase 2: var[row][*] = prior_var - sum_s partial[n][s][r]  (fixed order: deterministic).
+// var_cols = 1: one shared variance per test row (GPy); var_cols = O: (Ns, O), each column scaled by std_o^2 when the
+// fused output normaliser is on (reference denormalize_variance) or plainly replicated when it is off.
+__global__ void var_final_kernel(const double* __restrict__ partial, int nb, int S, double prior_var,
+                                 const double* __restrict__ ystats, int var_cols, double* __restrict__ var, int64_t row0,
+                                 int64_t Ns) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)nb * GPX_TILE) return;
+    const int n = (int)(e >> 7), r = (int)(e & 127);
+    double s = 0.0;
+    for (int k = 0; k < S; k++) s += partial[((int64_t)n * S + k) * GPX_TILE + r];
+    const int64_t row = row0 + e;
+    if (row < Ns) {
+        const double v = prior_var - s;
+        for (int o = 0; o < var_cols; o++) {
+            const double sd = ystats ? ystats[var_cols + o] : 1.0;   // ystats = [O means | O stds]; var_cols == O here
+            var[row * var_cols + o] = ystats ? v * (sd * sd) : v;
         }
     }
 }
@@ -368,9 +383,19 @@ void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, 
                                                                                   mean_const, ystats, mean, row0, Ns);
 }
 
-void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, double prior_var, const double* ystats, int var_cols, double* var,
-                           int64_t row0, int64_t Ns, cudaStream_t st) {
-    var_reduce_kernel<<<nbt, 256, 0, st>>>(Tt, nt, prior_var, ystats, var_cols, var, row0, Ns);
+int gpx_var_reduce_splits(int nbt, int nt, int num_sms) {
+    int S = (4 * num_sms + nbt - 1) / nbt;     // ~4 CTAs per SM in flight
+    if (S > nt) S = nt;
+    if (S > 64) S = 64;
+    return S < 1 ? 1 : S;
+}
+
+// `partial` holds nbt * S * 128 doubles (S = gpx_var_reduce_splits)
+void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, int S, double* partial, double prior_var, const double* ystats,
+                           int var_cols, double* var, int64_t row0, int64_t Ns, cudaStream_t st) {
+    var_partial_kernel<<<dim3(nbt, S), 256, 0, st>>>(Tt, nt, S, partial);
+    const int64_t total = (int64_t)nbt * GPX_TILE;
+    var_final_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(partial, nbt, S, prior_var, ystats, var_cols, var, row0, Ns);
 }
 
 void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double* out, cudaStream_t st) {

@@ -42,31 +42,77 @@ __device__ __forceinline__ void diag_apply(const double* __restrict__ inv_tile, 
 }
 
 // forward step J.  b, z: [O][Np].  grid.x CTAs stride over tiles I = J+1 .. nt-1.
+// Right-hand sides are handled kFwdRhs at a time: every tile of L (and the inverted diagonal tile) is read ONCE per group
+// and applied to all of the group's vectors from registers -- with one vector per pass (round 1) a multi-output alpha solve
+// or the latency-path variance of several test rows re-read L once per vector.
+constexpr int kFwdRhs = 8;
 __global__ void __launch_bounds__(256) fwd_step_kernel(TileMat L, const double* __restrict__ linv, int nt, int J,
                                                        double* __restrict__ b, double* __restrict__ z, int64_t Np, int O) {
-    __shared__ double sv_in[GPX_TILE], sz[GPX_TILE], scratch[GPX_TILE];
+    __shared__ double sv[kFwdRhs][GPX_TILE], sz[kFwdRhs][GPX_TILE], scratch[kFwdRhs][GPX_TILE];
     const int tid = threadIdx.x, r = tid & 127, half = tid >> 7;
-    for (int o = 0; o < O; o++) {
-        double* bo = b + (int64_t)o * Np;
-        diag_apply(linv + (int64_t)J * GPX_TILE_ELEMS, bo + (int64_t)J * GPX_TILE, false, sv_in, sz, scratch);
-        if (blockIdx.x == 0 && tid < GPX_TILE) z[(int64_t)o * Np + (int64_t)J * GPX_TILE + tid] = sz[tid];
+    const double* inv_tile = linv + (int64_t)J * GPX_TILE_ELEMS;
+    for (int o0 = 0; o0 < O; o0 += kFwdRhs) {
+        const int Oc = (O - o0 < kFwdRhs) ? (O - o0) : kFwdRhs;
+        // z_J = Linv_JJ b_J for the group (every CTA recomputes it: no grid-wide dependency)
+        for (int e = tid; e < Oc * GPX_TILE; e += 256) sv[e >> 7][e & 127] = b[(int64_t)(o0 + (e >> 7)) * Np + (int64_t)J * GPX_TILE + (e & 127)];
+        __syncthreads();
+        {
+            double acc[kFwdRhs];
+#pragma unroll
+            for (int o = 0; o < kFwdRhs; o++) acc[o] = 0.0;
+#pragma unroll
+            for (int kc = 0; kc < 8; kc++) {
+                const int ch = half * 8 + kc;
+                const double2* p = reinterpret_cast<const double2*>(inv_tile + ch * 1024 + r * 8);
+                const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+#pragma unroll
+                for (int o = 0; o < kFwdRhs; o++) {
+                    if (o < Oc) {
+                        const double* x = &sv[o][ch * 8];
+                        double s = acc[o];
+                        s = fma(v0.x, x[0], s); s = fma(v0.y, x[1], s); s = fma(v1.x, x[2], s); s = fma(v1.y, x[3], s);
+                        s = fma(v2.x, x[4], s); s = fma(v2.y, x[5], s); s = fma(v3.x, x[6], s); s = fma(v3.y, x[7], s);
+                        acc[o] = s;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < kFwdRhs; o++) if (o < Oc && half == 1) scratch[o][r] = acc[o];
+            __syncthreads();
+#pragma unroll
+            for (int o = 0; o < kFwdRhs; o++) if (o < Oc && half == 0) sz[o][r] = acc[o] + scratch[o][r];
+            __syncthreads();
+        }
+        if (blockIdx.x == 0)
+            for (int e = tid; e < Oc * GPX_TILE; e += 256) z[(int64_t)(o0 + (e >> 7)) * Np + (int64_t)J * GPX_TILE + (e & 127)] = sz[e >> 7][e & 127];
+        // b_I -= L_IJ z_J
         for (int I = J + 1 + blockIdx.x; I < nt; I += gridDim.x) {
             const double* tp = tile_ptr(L, I, J);
-            double s = 0.0;
+            double acc[kFwdRhs];
+#pragma unroll
+            for (int o = 0; o < kFwdRhs; o++) acc[o] = 0.0;
 #pragma unroll
             for (int kc = 0; kc < 8; kc++) {
                 const int ch = half * 8 + kc;
                 const double2* p = reinterpret_cast<const double2*>(tp + ch * 1024 + r * 8);
+                const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    double2 v = p[u];
-                    s = fma(v.x, sz[ch * 8 + 2 * u], s);
-                    s = fma(v.y, sz[ch * 8 + 2 * u + 1], s);
+                for (int o = 0; o < kFwdRhs; o++) {
+                    if (o < Oc) {
+                        const double* x = &sz[o][ch * 8];
+                        double s = acc[o];
+                        s = fma(v0.x, x[0], s); s = fma(v0.y, x[1], s); s = fma(v1.x, x[2], s); s = fma(v1.y, x[3], s);
+                        s = fma(v2.x, x[4], s); s = fma(v2.y, x[5], s); s = fma(v3.x, x[6], s); s = fma(v3.y, x[7], s);
+                        acc[o] = s;
+                    }
                 }
             }
-            if (half == 1) scratch[r] = s;
+#pragma unroll
+            for (int o = 0; o < kFwdRhs; o++) if (o < Oc && half == 1) scratch[o][r] = acc[o];
             __syncthreads();
-            if (half == 0) bo[(int64_t)I * GPX_TILE + r] -= s + scratch[r];
+#pragma unroll
+            for (int o = 0; o < kFwdRhs; o++)
+                if (o < Oc && half == 0) b[(int64_t)(o0 + o) * Np + (int64_t)I * GPX_TILE + r] -= acc[o] + scratch[o][r];
             __syncthreads();
         }
     }

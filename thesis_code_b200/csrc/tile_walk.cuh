@@ -3,7 +3,9 @@
 #pragma once
 #include "gpx_common.cuh"
 
-#define GPX_GEMM_STRIP 8   // output tile columns per rasterisation strip
+#define GPX_GEMM_STRIP 16  // default output tile columns per rasterisation strip (GemmJob.strip = 0): 16 B-operand panels stay hot in
+                           // L2 while the A row panels stream by once per strip (8 -> 16 measured +0.5 % at N = 60000, 32 slower)
+__host__ __device__ __forceinline__ int gpx_job_strip(const GemmJob& j) { return j.strip > 0 ? j.strip : GPX_GEMM_STRIP; }
 
 // Output-tile enumeration shared by producer and consumers: strips of GPX_GEMM_STRIP column ordinals, row-major inside a
 // strip, so CTAs running together share few operand panels (L2 reuse).  Invalid (above-diagonal) slots of a
@@ -15,7 +17,8 @@ struct TileWalk {
     int strip_m0, strip_w, strip_r0;
     long long strip_begin, strip_end;
     __host__ __device__ void set_strip(const GemmJob& j) {
-        strip_w = (GPX_GEMM_STRIP < ncols - strip_m0 ? GPX_GEMM_STRIP : ncols - strip_m0);
+        const int sw = gpx_job_strip(j);
+        strip_w = (sw < ncols - strip_m0 ? sw : ncols - strip_m0);
         strip_r0 = tri ? (i0 > gpx_job_col(j, strip_m0) ? i0 : gpx_job_col(j, strip_m0)) : i0;
         if (strip_r0 > i1) strip_r0 = i1;
     }
@@ -59,8 +62,9 @@ inline long long count_valid_tiles(const GemmJob& j) {
 
 inline long long count_slots(const GemmJob& j) {
     long long total = 0;
-    for (int m0 = 0; m0 < j.ncols; m0 += GPX_GEMM_STRIP) {
-        int w = (j.ncols - m0 < GPX_GEMM_STRIP) ? (j.ncols - m0) : GPX_GEMM_STRIP;
+    const int sw = gpx_job_strip(j);
+    for (int m0 = 0; m0 < j.ncols; m0 += sw) {
+        int w = (j.ncols - m0 < sw) ? (j.ncols - m0) : sw;
         int c0 = gpx_job_col(j, m0);
         int r0 = j.tri ? (j.i0 > c0 ? j.i0 : c0) : j.i0;
         if (r0 > j.i1) r0 = j.i1;

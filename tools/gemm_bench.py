@@ -1,4 +1,5 @@
-"""Isolated timing of the DMMA tile GEMM (gpx_debug_gemm, a development-only symbol that is not part of include/gpx.h)."""
+"""Isolated timing of the DMMA tile GEMM and the POTRF tile kernel through the development-only symbols gpx_debug_gemm /
+gpx_debug_potrf (exported only by `make -C thesis_code_b200/csrc DEBUG_API=1`)."""
 import ctypes, sys
 sys.path.insert(0, '.')
 from thesis_code_b200 import _gpx
@@ -8,10 +9,15 @@ f.restype = ctypes.c_double
 f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
 g = h.lib.gpx_debug_potrf; g.restype = ctypes.c_double; g.argtypes = [ctypes.c_void_p, ctypes.c_int]
 print("potrf_tile_kernel (128x128 Cholesky + inverse): %.1f us per launch" % g(h._h, 50))
-print("rows cols K overwrite chunk :   ms    TFLOP/s")
-for (rows, cols, K, ow, ch) in [(148, 64, 1, 0, 16), (148, 64, 2, 0, 16), (148, 64, 4, 0, 16), (148, 64, 8, 0, 16), (148, 64, 16, 0, 16),
-                                (148, 64, 4, 1, 16), (148, 64, 1, 1, 16), (148, 64, 4, 0, 1), (148, 64, 4, 0, 4), (148, 64, 4, 0, 64),
-                                (148, 8, 4, 0, 8), (148, 1, 4, 0, 1), (148, 1, 16, 0, 1), (148, 1, 64, 0, 1), (296, 1, 64, 0, 1)]:
-    ms = f(h._h, rows, cols, K, ow, ch, 5)
-    fl = 2.0 * 128 ** 3 * rows * cols * K
-    print("%4d %4d %3d %d %3d : %8.3f  %6.2f" % (rows, cols, K, ow, ch, ms, fl / ms / 1e9))
+shapes = [(148, 64, 1, 0, 16), (148, 64, 2, 0, 16), (148, 64, 4, 0, 16), (148, 64, 8, 0, 16), (148, 64, 16, 0, 16),
+          (148, 64, 4, 1, 16), (148, 64, 1, 1, 16), (148, 64, 4, 0, 1), (148, 64, 4, 0, 4), (148, 64, 4, 0, 64),
+          (148, 8, 4, 0, 8), (148, 1, 4, 0, 1), (148, 1, 16, 0, 1), (148, 1, 64, 0, 1), (296, 1, 64, 0, 1), (131, 300, 16, 0, 16)]
+print("rows cols K overwrite chunk :  stagger off: ms TFLOP/s | stagger on: ms TFLOP/s")
+for (rows, cols, K, ow, ch) in shapes:
+    out = []
+    for stag in (0, 1):
+        h.set_option("gemm_stagger", stag)
+        ms = min(f(h._h, rows, cols, K, ow, ch, 5) for _ in range(2))
+        fl = 2.0 * 128 ** 3 * rows * cols * K
+        out.append((ms, fl / ms / 1e9))
+    print("%4d %4d %3d %d %3d : %8.3f  %6.2f | %8.3f  %6.2f" % (rows, cols, K, ow, ch, out[0][0], out[0][1], out[1][0], out[1][1]))
