@@ -26,6 +26,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) would land there too
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 FP64_DMMA_PEAK_TFLOPS = 36.96   # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.txt)
 METRIC = "exact-GP fit+predict FP64 throughput (algorithmic N^3/3 + N^2*N* flop per fit+predict)"

@@ -44,8 +44,39 @@ static int check(const GemmJob& job, int chunk, const char* what) {
     return 0;
 }
 
+// "panel solve" jobs (GemmJob::rowwise): with chunk = ncols every CTA must own exactly one half tile row and visit its
+// columns in descending order (the in-place update relies on both), and the contraction range must stop at the diagonal.
+static int check_rowwise(int nb, int p0, int w) {
+    GemmJob j{};
+    j.tri = 0; j.i0 = 0; j.i1 = nb; j.ncols = w; j.jbase = p0; j.jW = GPX_JW_CONTIG; j.jstride = 0; j.k0 = p0; j.k1 = p0 + w; j.rowwise = 1;
+    const int chunk = w;
+    if (check(j, chunk, "rowwise")) return 1;
+    const long long slots = 2 * count_slots(j);
+    if (slots != 2LL * nb * w) { printf("rowwise: slot count\n"); return 1; }
+    long long steps = 0;
+    for (long long b = 0; b < slots / chunk; b++) {
+        TileWalk walk; walk.init(j);
+        int lastJ = 1 << 30, row = -1;
+        for (long long t = b * chunk; t < (b + 1) * chunk; t++) {
+            int I, J, half; bool valid;
+            if (!walk.locate(j, t, I, J, half, valid) || !valid) { printf("rowwise: missing slot\n"); return 1; }
+            if (row < 0) row = I;
+            if (I != row || I != (int)(b / 2) || half != (int)(b & 1)) { printf("rowwise: CTA %lld touches row %d half %d\n", b, I, half); return 1; }
+            if (J >= lastJ) { printf("rowwise: columns not strictly descending\n"); return 1; }
+            lastJ = J;
+            if (gpx_job_k1(j, J) != J + 1) { printf("rowwise: k range of column %d ends at %d\n", J, gpx_job_k1(j, J)); return 1; }
+            if (half == 0) steps += gpx_job_k1(j, J) - j.k0;
+        }
+    }
+    if (steps != count_steps(j) || steps != (long long)nb * w * (w + 1) / 2) { printf("rowwise: step count %lld vs %lld\n", steps, count_steps(j)); return 1; }
+    return 0;
+}
+
 int main() {
     int bad = 0, cases = 0;
+    for (int nb : {1, 2, 131, 148})
+        for (int p0 : {0, 16, 37})
+            for (int w : {1, 2, 4, 13, 16}) { bad += check_rowwise(nb, p0, w); cases++; }
     const int chunks[] = {1, 2, 3, 7, 8, 16, 32, 33};
     for (int chunk : chunks) {
         for (int nt : {1, 2, 5, 8, 9, 17, 40, 71}) {

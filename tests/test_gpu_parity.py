@@ -653,3 +653,32 @@ def test_caller_stream_ordering_and_device_pointers(gpu_handle):
     gpu_handle.predict_device(dXs.data_ptr(), 300, dmean.data_ptr(), dvar.data_ptr(), True)
     gpu_handle.set_stream(None)
     assert np.array_equal(dmean.cpu().numpy(), ref_mean) and np.array_equal(dvar.cpu().numpy(), ref_var)
+
+
+@pytest.mark.parametrize("cfg,N,Ns,W", [("C3", 3000, 1500, 4), ("C4", 5000, 9000, 16), ("C5", 2100, 700, 5), ("C2", 1300, 300, 13)])
+def test_panel_inverse_variance_solve_matches_stepwise_and_oracle(cfg, N, Ns, W):
+    """In-panel variance solve through the inverted W x W-tile diagonal blocks (one row-wise GEMM per panel, option
+    "panel_inverse") vs the step-wise TRSM path and the oracle, incl. a ragged last panel and a refit in between."""
+    c = synthetic.make_config(cfg, N=N, Ns=Ns)
+    kw = c["model"]["kwargs"]
+    m = GPModel.from_config(kw)
+    h = m._get_handle()
+    h.set_option("outer_tiles", W)
+    m.init(c["X"], c["Y"])
+    om = o.OracleGPModel(kernel=kw["kernel"], noise_prior=kw["noise_prior"]); om.init(c["X"], c["Y"])
+    omean, ovar = om.get_statistics(c["Xs"], full_cov=False)
+    out = {}
+    for mode in (0, 1, 0, 1):
+        h.set_option("panel_inverse", mode)
+        l0 = h.launch_count()
+        mean, var = m.get_statistics(c["Xs"], full_cov=False)
+        out.setdefault(mode, []).append((mean, var, h.launch_count() - l0))
+        assert normwise(mean, omean) < TOL and normwise(var, ovar) < TOL, (cfg, mode)
+    assert np.array_equal(out[1][0][1], out[1][1][1])                       # cached blocks: bit-identical repeat
+    assert out[1][1][2] < out[0][1][2]                                      # fewer launches than the step-wise path
+    assert normwise(out[1][0][1], out[0][0][1]) < 1e-10
+    m.init(c["X"][: N - 200], c["Y"][: N - 200])                           # refit: the blocks must be rebuilt
+    om.init(c["X"][: N - 200], c["Y"][: N - 200])
+    mean, var = m.get_statistics(c["Xs"], full_cov=False)
+    omean, ovar = om.get_statistics(c["Xs"], full_cov=False)
+    assert normwise(mean, omean) < TOL and normwise(var, ovar) < TOL

@@ -8,13 +8,18 @@
 // update (A = B = factored panel), the panel TRSM (B = inverted diagonal tile) and the predictive-variance
 // triangular solve (A = transposed cross-kernel workspace, B = L).
 //
-// Structure (TWO co-resident CTAs per SM, 160 threads each, one 64x128 HALF tile (64 rows) per work slot):
-//   * warp 4 lane 0 = producer: for every output half tile and every 16-wide K slice issues two 4 KB (A: the 64 rows
+// Structure (TWO co-resident CTAs per SM, 288 threads each, one 64x128 HALF tile (64 rows) per work slot):
+//   * the last warp's lane 0 = producer: for every output half tile and every 16-wide K slice issues two 4 KB (A: the 64 rows
 //     of this half, one per 8-column chunk) and one 16 KB (B: 128 rows) 1-D TMA bulk copies
 //     (cp.async.bulk.shared::cluster.global, SASS UBLKCP) into a 4-stage shared-memory ring (96 KB per CTA), signalled
 //     through mbarriers (full/empty);
-//   * warps 0..3 = consumers, 1 (M) x 4 (N), each owning a 64x32 accumulator block = 8x4 DMMA 8x8 fragments held
-//     in registers (64 doubles / thread).  Per 8-k chunk a warp issues 12 conflict-free LDS.128 and 64 DMMA.
+//   * warps 0..7 = consumers, 2 (M) x 4 (N), each owning a 32x32 accumulator block = 4x4 DMMA 8x8 fragments held
+//     in registers (32 doubles / thread).  Per 8-k chunk a warp issues 8 conflict-free LDS.128 and 32 DMMA.
+//     (Round 1 used 4 warps of 64x32: four warps per SM sub-partition instead of two hide the LDS -> DMMA latency
+//     better where the pipeline is short -- K = 1 tile 31.5 -> 32.6, K = 4 tiles 34.5 -> 35.1 TFLOP/s, K = 16 unchanged
+//     at 35.9 (tools/gemm_bench.py, profiles/r02_gemm_warps.txt) -- which is what the sharded runs (K = 4) live on.)
+//   * GemmJob::rowwise = "panel solve" mode: one tile row per CTA, columns in descending order, contraction cut at the
+//     diagonal, in place -- the in-panel part of the variance solve against the inverted diagonal block (gpx_api.cu).
 //   * accumulate mode initialises the accumulators with the old C half tile (coalesced 512 B fragment loads; the
 //     producer has already pulled it into L2 with a bulk prefetch) and feeds NEGATED A fragments: store-only epilogue.
 //   * Why two small CTAs instead of one 128x128 CTA (round-1 first version): the per-tile prologue/epilogue (C load
@@ -39,7 +44,12 @@ constexpr int kOperBytes = GPX_TILE * kStageK * 8;       // B: 128 rows x 16 k =
 constexpr int kHalf = 64;                                // output rows (= A rows) per work slot
 constexpr int kAChunkBytes = kHalf * 8 * 8;              // A: 64 rows x one 8-column chunk = 4 KB
 constexpr int kStageBytes = 2 * kAChunkBytes + kOperBytes;   // 24 KB: [A chunk 0][A chunk 1][B]
-constexpr int kConsumerWarps = 4;
+#ifndef GPX_GEMM_WARPS
+#define GPX_GEMM_WARPS 8
+#endif
+constexpr int kConsumerWarps = GPX_GEMM_WARPS;           // 4: 1 (M) x 4 (N) warps of 64x32;  8: 2 (M) x 4 (N) warps of 32x32
+constexpr int kWarpRows = kHalf / (kConsumerWarps / 4);  // accumulator rows per warp
+constexpr int kFragI = kWarpRows / 8;                    // 8x8 accumulator fragments per warp along M
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStages * 8 + 128;
 #ifndef GPX_WAR_FENCE_MODE
@@ -114,7 +124,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob jo
                 if (!valid) continue;
                 // the consumers will read-modify-write C(I,J) when they reach it: pull the tile into L2 now
                 if (!kOverwrite && half == 0) bulk_prefetch_l2(tile_ptr(job.C, I, J), GPX_TILE_BYTES);
-                for (int kb = job.k0; kb < job.k1; kb++) {
+                const int k_hi = gpx_job_k1(job, J);
+                for (int kb = job.k0; kb < k_hi; kb++) {
                     const double* a = tile_ptr(job.A, I, kb) + half * kHalf * 8;
                     const double* b = job.bdiag ? tile_ptr(job.B, kb, kb) : tile_ptr(job.B, J, kb);
                     for (int s = 0; s < nslice; s++) {
@@ -132,13 +143,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob jo
         }
     } else {
         // ---------------- consumers ----------------
-        const int wn = warp;   // 4 warps side by side along N, each 64 rows x 32 columns
+        const int wn = warp & 3, wm = warp >> 2;   // warps side by side along N (32 columns each), stacked along M
         const int g = lane >> 2, tq = lane & 3;
         // fragment offsets inside an 8-k chunk ([row][8] doubles)
-        const int a_off = g * 8 + 2 * tq;
+        const int a_off = (wm * kWarpRows + g) * 8 + 2 * tq;
         const int b_off = (wn * 32 + g) * 8 + 2 * tq;
-        // accumulator fragment (i,j) of row half h lives at tile offset  (wn*4 + j) * 1024 + (h*64 + i*8 + g) * 8 + 2*tq
-        const int c_off0 = (wn * 4) * 1024 + g * 8 + 2 * tq;
+        // accumulator fragment (i,j) of row half h lives at tile offset  (wn*4 + j) * 1024 + (h*64 + wm*rows + i*8 + g) * 8 + 2*tq
+        const int c_off0 = (wn * 4) * 1024 + (wm * kWarpRows + g) * 8 + 2 * tq;
 
         for (long long t = t_begin; t < t_end; t++) {
             int I, J, half; bool valid;
@@ -146,22 +157,23 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob jo
             if (!valid) continue;
             double* ctile = tile_ptr(job.C, I, J);
             const int c_off = c_off0 + half * kHalf * 8;
-            double acc[8][4][2];
+            double acc[kFragI][4][2];
             if (kOverwrite) {
 #pragma unroll
-                for (int i = 0; i < 8; i++)
+                for (int i = 0; i < kFragI; i++)
 #pragma unroll
                     for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++)
+                for (int i = 0; i < kFragI; i++)
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         double2 v = __ldcg(reinterpret_cast<const double2*>(ctile + c_off + j * 1024 + i * 64));
                         acc[i][j][0] = v.x; acc[i][j][1] = v.y;
                     }
             }
-            for (int kb = job.k0; kb < job.k1; kb++) {
+            const int k_hi = gpx_job_k1(job, J);
+            for (int kb = job.k0; kb < k_hi; kb++) {
                 for (int s = 0; s < nslice; s++) {
                     mbar_wait(&full[stage], phase);
                     const double* As = reinterpret_cast<const double*>(smem + stage * kStageBytes);
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob jo
                         for (int j = 0; j < 4; j++)
                             bf[j] = *reinterpret_cast<const double2*>(Bs + ch * 1024 + b_off + j * 64);
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
+                        for (int i = 0; i < kFragI; i++) {
                             double2 af = *reinterpret_cast<const double2*>(As + ch * (kHalf * 8) + a_off + i * 64);
                             if (!kOverwrite) { af.x = -af.x; af.y = -af.y; }
 #pragma unroll
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob jo
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < kFragI; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                     *reinterpret_cast<double2*>(ctile + c_off + j * 1024 + i * 64) =
@@ -233,7 +245,9 @@ long long gpx_launch_gemm(const GemmJob& job_in, int num_sms, cudaStream_t st, i
     const int resident = 2 * num_sms;
     const int max_chunk = 2 * (job.chunk < 1 ? 16 : (job.chunk > 64 ? 64 : job.chunk));  // caller's cap is in full tiles
     long long chunk = 1;
-    if (slots > resident) {
+    if (job.rowwise) {
+        chunk = job.ncols;         // one half tile row per CTA (the in-place panel solve relies on it)
+    } else if (slots > resident) {
         const double slot_us = 17.0 * (job.k1 - job.k0), ovh_us = 4.0;   // a half tile at half an SM's rate
         double best = 1e300;
         for (long long c = 1; c <= max_chunk; c++) {
@@ -250,5 +264,5 @@ long long gpx_launch_gemm(const GemmJob& job_in, int num_sms, cudaStream_t st, i
     else
         gemm_dmma_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(job);
     if (launch_counter) (*launch_counter)++;
-    return count_valid_tiles(job) * (job.k1 - job.k0);
+    return count_steps(job);
 }

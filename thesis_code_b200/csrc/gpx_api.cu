@@ -365,7 +365,8 @@ void gpx_destroy(gpx_t* h) {
     DevBuf* all[] = {&h->Xs, &h->xsq, &h->ls, &h->L, &h->linv, &h->coloff, &h->vcoloff, &h->linv_coloff, &h->resid,
                      &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->gbuf[0], &h->gbuf[1], &h->cache,
                      &h->ucoloff, &h->Tt,
-                     &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar, &h->sp, &h->xstats, &h->ystats, &h->var_partial};
+                     &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar, &h->sp, &h->xstats, &h->ystats, &h->var_partial, &h->minv, &h->minv_coloff,
+                     &h->ywork, &h->ywork_coloff};
     for (DevBuf* b : all) release(h, *b);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->pin) cudaFreeHost(h->pin);
@@ -431,6 +432,7 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "nccl_lo_ctas")) { h->nccl_lo_ctas = (int)value; return 0; }  // takes effect at gpx_comm_init
     if (!strcmp(name, "trace")) { h->trace = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_max_chunk")) { h->gemm_max_chunk = (int)value; return 0; }
+    if (!strcmp(name, "panel_inverse")) { h->panel_inverse = (int)value; return 0; }   // -1 auto, 0 off, 1 on
     if (!strcmp(name, "gemm_strip")) { if (value < 0 || value > 64) return fail(h, -1, "gemm_strip out of range"); h->gemm_strip = (int)value; return 0; }
     if (!strcmp(name, "reserve_rows")) { if (value < 0) return fail(h, -1, "bad reserve_rows"); h->reserve_rows = value; return 0; }
     if (!strcmp(name, "predict_graph")) { h->predict_graph = value ? 1 : 0; h->gen++; return 0; }
@@ -714,23 +716,75 @@ int gpx_lml(gpx_t* h, double* lml, double* logdet, double* quad) {
 // (upper_rows: Tt is known to be upper triangular in tile terms -- rows >= p1 are still zero -- so they are skipped)
 }  // extern "C"
 
-void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows) {
-    const int nt = h->nt, p0 = panel_begin(h, p), p1 = panel_end(h, p);
-    const int nb = (upper_rows && p1 < nb_in) ? p1 : nb_in;
+// in-panel part of the blocked solve  X <- X L^-T  for the tile rows [0, nb) of X and the tile columns [p0, p1): per
+// column a TRSM against the inverted diagonal tile, then a rank-128 update of the panel's remaining columns
+static void trsm_inner_stepwise(gpx_t* h, TileMat X, int nb, TileMat P, int p0, int p1) {
     TileMat Li = linvmat(h);
     for (int k = p0; k < p1; k++) {
         GemmJob t{};
-        t.A = Tt; t.B = Li; t.C = Tt;
+        t.A = X; t.B = Li; t.C = X;
         t.tri = 0; t.i0 = 0; t.i1 = nb; t.ncols = 1; t.jbase = k; t.jW = GPX_JW_CONTIG; t.jstride = 0;
         t.k0 = k; t.k1 = k + 1; t.bdiag = 1; t.overwrite = 1;
         gemm(h, t, h->st);
         if (k + 1 < p1) {
             GemmJob u{};
-            u.A = Tt; u.B = P; u.C = Tt;
+            u.A = X; u.B = P; u.C = X;
             u.tri = 0; u.i0 = 0; u.i1 = nb; u.ncols = p1 - (k + 1); u.jbase = k + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
             u.k0 = k; u.k1 = k + 1; u.bdiag = 0; u.overwrite = 0;
             gemm(h, u, h->st);
         }
+    }
+}
+
+// Inverse of every panel's triangular diagonal block (W x W tiles), M_p = L(p,p)^-1, kept as a block-diagonal packed-lower
+// tile matrix.  With it the in-panel part of the solve is ONE row-wise GEMM per panel and batch, X(:, panel) <- X(:, panel)
+// M_p^T with K up to W tiles, instead of 2 W - 1 launches at K = 1 tile (which run at ~85 % of the DMMA rate at best and
+// pay a launch ramp and tail each): at BASELINE config C4 the in-panel steps are 3.5 % of the variance solve's flops but
+// cost ~6 % of its time.  Built lazily by the first large predict after a fit: Y = M_p^T from the step-wise solve applied
+// to an identity block, then transposed tile by tile (the tile GEMM computes A B^T only).
+static int ensure_panel_inverse(gpx_t* h) {
+    if (h->minv_gen == h->gen && h->minv.p) return 0;
+    const int nt = h->nt, W = h->W, np = h->npanels;
+    std::vector<int64_t> moff(nt), yoff(nt);
+    int64_t tiles = 0;
+    for (int c = 0; c < nt; c++) {
+        const int p1 = panel_end(h, c / W);
+        moff[c] = tiles * GPX_TILE_ELEMS;
+        tiles += p1 - c;
+        yoff[c] = (int64_t)(c % W) * W * GPX_TILE_ELEMS;
+    }
+    int rc;
+    if ((rc = ensure(h, h->minv, (size_t)tiles * GPX_TILE_BYTES)) || (rc = ensure(h, h->minv_coloff, (size_t)nt * 8)) ||
+        (rc = ensure(h, h->ywork, (size_t)W * W * GPX_TILE_BYTES)) || (rc = ensure(h, h->ywork_coloff, (size_t)nt * 8))) return rc;
+    GPX_CUDA(h, cudaMemcpyAsync(h->minv_coloff.p, moff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
+    GPX_CUDA(h, cudaMemcpyAsync(h->ywork_coloff.p, yoff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
+    GPX_CUDA(h, cudaStreamSynchronize(h->st));   // moff / yoff are host temporaries
+    TileMat Y{ptr<double>(h->ywork), ptr<int64_t>(h->ywork_coloff), 0};
+    TileMat M{ptr<double>(h->minv), ptr<int64_t>(h->minv_coloff), 1};
+    for (int p = 0; p < np; p++) {
+        const int p0 = panel_begin(h, p), p1 = panel_end(h, p);
+        gpx_launch_identity_block(Y, p1 - p0, p0, h->st);
+        trsm_inner_stepwise(h, Y, p1 - p0, lmat(h), p0, p1);
+        gpx_launch_transpose_block(Y, M, p0, p1 - p0, h->st);
+        h->launches += 2;
+    }
+    h->minv_gen = h->gen;
+    return 0;
+}
+
+// one panel step of the blocked variance solve  Tt <- Tt L^-T  for nb test tiles (rows of Tt), L operand = P
+// (upper_rows: Tt is known to be upper triangular in tile terms -- rows >= p1 are still zero -- so they are skipped)
+void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows) {
+    const int nt = h->nt, p0 = panel_begin(h, p), p1 = panel_end(h, p);
+    const int nb = (upper_rows && p1 < nb_in) ? p1 : nb_in;
+    if (h->minv_active && !upper_rows) {
+        GemmJob t{};   // Tt(:, panel) <- Tt(:, panel) M_p^T, in place, one tile row per CTA (see GemmJob::rowwise)
+        t.A = Tt; t.B = TileMat{ptr<double>(h->minv), ptr<int64_t>(h->minv_coloff), 1}; t.C = Tt;
+        t.tri = 0; t.i0 = 0; t.i1 = nb; t.ncols = p1 - p0; t.jbase = p0; t.jW = GPX_JW_CONTIG; t.jstride = 0;
+        t.k0 = p0; t.k1 = p1; t.bdiag = 0; t.overwrite = 1; t.rowwise = 1;
+        gemm(h, t, h->st);
+    } else {
+        trsm_inner_stepwise(h, Tt, nb, P, p0, p1);
     }
     if (p1 < nt) {
         GemmJob u{};
@@ -852,6 +906,12 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
         Tt = TileMat{ptr<double>(h->Tt), ptr<int64_t>(h->tt_coloff), 0};
     }
     const double prior_var = h->variance + (include_noise ? h->noise : 0.0);
+    // in-panel solve through the inverted diagonal blocks: pays when there are enough test tiles to amortise building them
+    h->minv_active = 0;
+    if (var && G == 1 && h->W >= 2 && (h->panel_inverse == 1 || (h->panel_inverse < 0 && total_tiles >= 64))) {
+        if ((rc = ensure_panel_inverse(h))) return rc;
+        h->minv_active = 1;
+    }
 
     for (int b = 0; b < nbatch; b++) {
         const int t0 = my_t0 + b * per;
@@ -891,6 +951,7 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
             }
         }
     }
+    h->minv_active = 0;
     if (G > 1) {
         GPX_NCCL(h, nccl().AllReduce(dmean, dmean, (size_t)Ns * O, ncclDouble, ncclSum, h->comm, h->st));
         if (var) GPX_NCCL(h, nccl().AllReduce(dvar, dvar, (size_t)Ns * var_cols, ncclDouble, ncclSum, h->comm, h->st));

@@ -84,6 +84,10 @@ struct GemmJob {
     int overwrite;     // 1: C = +A*B^T ; 0: C -= A*B^T
     int chunk;         // in: cap on output-tile slots per CTA (0 = default 16); the launcher overwrites it with its choice
     int strip;         // output tile columns per rasterisation strip (0 = default, see tile_walk.cuh)
+    int rowwise;       // 1: "panel solve" mode -- one strip of all ncols columns, each CTA owns ONE half tile row (64 rows) and
+                       // walks its columns in DESCENDING order with the contraction cut at the diagonal, k in [k0, min(k1, J+1)):
+                       //   C(I, J) = sum_{k <= J} A(I, k) B(J, k)^T  written IN PLACE over A (column J is only read by columns >= J,
+                       // which the same CTA has already finished).  B = inverse of the panel's triangular diagonal block.
 };
 #define GPX_JW_CONTIG (1 << 28)
 __host__ __device__ __forceinline__ int gpx_job_col(const GemmJob& j, int m) {

@@ -37,6 +37,8 @@ void gpx_launch_resid(const double* Y, int64_t N, int64_t Np, int O, double mean
                       cudaStream_t st);
 void gpx_launch_untranspose(const double* in, int64_t N, int64_t Np, int O, double* out, cudaStream_t st);
 void gpx_launch_identity_tiles(TileMat T, int nt, cudaStream_t st);
+void gpx_launch_identity_block(TileMat T, int w, int j0, cudaStream_t st);            // T(i, j0 + j) = (i == j) I, i, j < w
+void gpx_launch_transpose_block(TileMat Y, TileMat M, int p0, int w, cudaStream_t st);  // M(p0+j, p0+k) = Y(k, p0+j)^T, k <= j < w
 void gpx_launch_lml_grad(TileMat Kinv, int nt, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
                          double variance, double rdiv, const double* ls, int n_ls, const double* alpha, int O, int64_t Np,
                          double* partial, double* out, cudaStream_t st);
@@ -92,6 +94,11 @@ struct gpx_handle {
     int gemm_max_chunk = 0;               // 0 = auto: 16 on one GPU, 4 when sharded (shorter CTAs let the panel
                                           // factorisation and NCCL kernels of the other streams in sooner)
     int gemm_strip = 0;                   // option "gemm_strip": rasterisation strip width of the tile GEMM (0 = default)
+    int panel_inverse = -1;               // option "panel_inverse": in-panel variance solve through inverted diagonal blocks
+                                          // (-1 auto: predicts with >= 64 test tiles on one GPU; 0 off; 1 on)
+    int minv_active = 0;                  // set by gpx_predict around its batch loop
+    uint64_t minv_gen = 0;                // fit generation the inverted blocks belong to
+    DevBuf minv, minv_coloff, ywork, ywork_coloff;
     int trace = 0;                        // 1: per-panel timeline events during the Cholesky (gpx_trace)
     std::vector<cudaEvent_t> tev;         // 6 per panel + 1 base, timing enabled
     std::vector<float> trace_ms;          // 6 per panel: factor start, factor end, panel ready, (a) end, fwd end, (b) end

@@ -570,6 +570,43 @@ static void gpx_grad_init_attr() {
                          (int)((2 * GPX_TILE * (kMaxD | 1) + 2 * GPX_TILE + 8 * (2 + kMaxD)) * sizeof(double)));
 }
 
+namespace {
+// T(i, j0 + j) <- (i == j) ? I : 0   for i, j < w   (rows are 0-based tile rows of a rectangular tile matrix)
+__global__ void identity_block_kernel(TileMat T, int j0) {
+    const int i = blockIdx.x, j = blockIdx.y;
+    double* tp = tile_ptr(T, i, j0 + j);
+    for (int e = threadIdx.x; e < GPX_TILE_ELEMS; e += blockDim.x) {
+        int r = (e >> 3) & 127, c = (e >> 10) * 8 + (e & 7);
+        tp[e] = (i == j && r == c) ? 1.0 : 0.0;
+    }
+    gpx_publish_for_async_proxy();
+}
+
+// M(p0 + j, p0 + k) <- Y(k, p0 + j)^T for k <= j < w.  grid (w (w + 1) / 2 tile pairs, 16 sub-blocks of 32 x 32).
+__global__ void __launch_bounds__(256) transpose_block_kernel(TileMat Y, TileMat M, int p0, int w) {
+    __shared__ double sm[32][33];
+    int j = 0, rem = blockIdx.x;
+    while (rem > j) { rem -= j + 1; j++; }       // pair index -> (j, k = rem), k <= j
+    const int k = rem;
+    const double* src = tile_ptr(Y, k, p0 + j);   // element (r, c) of Y's tile (k, j)
+    double* dst = tile_ptr(M, p0 + j, p0 + k);    // element (c, r) of M's tile (j, k)
+    const int br = (blockIdx.y >> 2) * 32, bc = (blockIdx.y & 3) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int rr = ty; rr < 32; rr += 8) sm[rr][tx] = src[gpx_tile_idx(br + rr, bc + tx)];
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) dst[gpx_tile_idx(bc + rr, br + tx)] = sm[tx][rr];
+    gpx_publish_for_async_proxy();
+}
+}  // namespace
+
+void gpx_launch_identity_block(TileMat T, int w, int j0, cudaStream_t st) {
+    identity_block_kernel<<<dim3(w, w), 256, 0, st>>>(T, j0);
+}
+
+void gpx_launch_transpose_block(TileMat Y, TileMat M, int p0, int w, cudaStream_t st) {
+    transpose_block_kernel<<<dim3(w * (w + 1) / 2, 16), 256, 0, st>>>(Y, M, p0, w);
+}
+
 void gpx_launch_identity_tiles(TileMat T, int nt, cudaStream_t st) {
     dim3 grid(nt, nt);
     identity_tiles_kernel<<<grid, 256, 0, st>>>(T, nt);

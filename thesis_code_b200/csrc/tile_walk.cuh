@@ -5,7 +5,12 @@
 
 #define GPX_GEMM_STRIP 16  // default output tile columns per rasterisation strip (GemmJob.strip = 0): 16 B-operand panels stay hot in
                            // L2 while the A row panels stream by once per strip (8 -> 16 measured +0.5 % at N = 60000, 32 slower)
-__host__ __device__ __forceinline__ int gpx_job_strip(const GemmJob& j) { return j.strip > 0 ? j.strip : GPX_GEMM_STRIP; }
+__host__ __device__ __forceinline__ int gpx_job_strip(const GemmJob& j) {
+    if (j.rowwise) return j.ncols;     // one strip of all columns
+    return j.strip > 0 ? j.strip : GPX_GEMM_STRIP;
+}
+// contraction range of output tile column J
+__host__ __device__ __forceinline__ int gpx_job_k1(const GemmJob& j, int J) { return (j.rowwise && J + 1 < j.k1) ? J + 1 : j.k1; }
 
 // Output-tile enumeration shared by producer and consumers: strips of GPX_GEMM_STRIP column ordinals, row-major inside a
 // strip, so CTAs running together share few operand panels (L2 reuse).  Invalid (above-diagonal) slots of a
@@ -31,6 +36,18 @@ struct TileWalk {
     }
     // t counts HALF-tile slots: tile slot t >> 1, row half t & 1.  Returns false when t is past the end.
     __host__ __device__ bool locate(const GemmJob& j, long long t2, int& I, int& J, int& half, bool& valid) {
+        if (j.rowwise) {
+            // panel-solve mode: slot order (row, half, column descending); a CTA's chunk of ncols slots is one half tile row
+            const int w = ncols;
+            if (t2 >= 2LL * (i1 - i0) * w) return false;
+            const long long r = t2 / (2 * w);
+            const int rem = (int)(t2 - r * 2 * w);
+            half = rem / w;
+            I = i0 + (int)r;
+            J = gpx_job_col(j, w - 1 - (rem - half * w));
+            valid = true;
+            return true;
+        }
         half = (int)(t2 & 1);
         const long long t = t2 >> 1;
         while (t >= strip_end) {
@@ -58,6 +75,14 @@ inline long long count_valid_tiles(const GemmJob& j) {
         if (r0 < j.i1) total += j.i1 - r0;
     }
     return total;
+}
+
+// (tile, k-tile) steps of a job: what the launcher reports as work (2 * 128^3 flop each)
+inline long long count_steps(const GemmJob& j) {
+    if (!j.rowwise) return count_valid_tiles(j) * (j.k1 - j.k0);
+    long long per_row = 0;
+    for (int m = 0; m < j.ncols; m++) { int J = gpx_job_col(j, m); int k1 = gpx_job_k1(j, J); if (k1 > j.k0) per_row += k1 - j.k0; }
+    return per_row * (j.i1 - j.i0);
 }
 
 inline long long count_slots(const GemmJob& j) {
