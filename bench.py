@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--Ns", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="one extra (untimed) fit with the per-panel timeline of the Cholesky")
     ap.add_argument("--budget-s", type=float, default=float(os.environ.get("GPX_BENCH_BUDGET_S", "600")),
                     help="wall-clock budget of the whole run: the number of full-size timed steps is cut to fit it")
     args = ap.parse_args()
@@ -331,6 +332,25 @@ def main():
         check["what"] = ("solve_residual = ||Ky alpha - y|| / ||y||, factor_residual = ||L L^T v - Ky v|| / ||Ky v|| with Ky rebuilt "
                          "tile-wise by the K-build kernels; var_min / var_max over all test points of the last timed step")
 
+    # ---- optional: per-panel timeline of one extra factorisation (outside every timed region) --------------------------
+    trace_summary = None
+    if args.trace:
+        h.set_option("trace", 1)
+        h.fit_device(dX.data_ptr(), N, d, dY.data_ptr(), 1, kid, variance, ls, noise, ARD=ard)
+        tr = h.trace()            # (npanels, 6): factor start, factor end, panel ready on U, next-panel update done, fwd done, trailing done
+        h.set_option("trace", 0)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.save(os.path.join(ROOT, "gpurun_out", "trace_%dgpu_rank%d.npy" % (world, rank)), tr)
+        ready, bend = tr[:, 2], tr[:, 5]
+        waits = np.maximum(0.0, ready[1:] - bend[:-1])          # stream U idle before panel p is ready
+        own = tr[:, 1] > 0
+        trace_summary = {"panels": int(tr.shape[0]), "cholesky_ms": float(bend[-1]), "update_stream_wait_ms": float(waits.sum()),
+                         "update_stream_wait_frac": float(waits.sum() / bend[-1]), "panels_with_wait_over_50us": int((waits > 0.05).sum()),
+                         "owner_factor_ms_mean": float((tr[own, 1] - tr[own, 0]).mean()) if own.any() else None,
+                         "what": "wait = time the update stream sits idle between finishing the trailing update of panel p-1 and "
+                                 "panel p being ready (factored + broadcast); rank 0's view"}
+        barrier()
+
     # ---- e2e: the public GPModel API with host numpy buffers (H2D + D2H inside the timed region) ----------------
     model = GPModel.from_config(cfg["model"]["kwargs"])
     model.device = local_rank
@@ -402,7 +422,7 @@ def main():
             "backward_solve_gbs": (8.0 * N * (N + 1) / 2 / max(world, 1)) / (phases["solve"] * 1e-3) / 1e9,
             "kstar_gevals_per_s": (float(N) * Ns / max(world, 1)) / (phases["predict_kstar"] * 1e-3) / 1e9 if phases.get("predict_kstar", 0) > 0 else None,
             "hbm_peak_gbs": peaks.get("hbm_gbs"),
-            "roofline": roofline, "cpu_baseline": cpu, "check": check,
+            "roofline": roofline, "cpu_baseline": cpu, "check": check, "trace": trace_summary,
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": "GPModel.init(X, Y) + get_statistics(Xtest, full_cov=False) on numpy arrays"},

@@ -71,6 +71,15 @@ __device__ __forceinline__ double gpx_k_of_r(int kernel_id, double variance, dou
     }
 }
 
+// the same, selected at compile time (the tile builders are instantiated per kernel: no per-element dispatch)
+template <int KID>
+__device__ __forceinline__ double gpx_k_of_r_t(double variance, double r) {
+    if (KID == 0) return variance * exp(-0.5 * (r * r));
+    if (KID == 1) { const double s5 = 2.23606797749978969641; return variance * (1.0 + s5 * r + (5.0 / 3.0) * (r * r)) * exp(-s5 * r); }
+    if (KID == 2) { const double s3 = 1.73205080756887729353; return variance * (1.0 + s3 * r) * exp(-s3 * r); }
+    return variance * exp(-r);
+}
+
 // ---- launchers implemented in the .cu files (all asynchronous on `st`) -------------------------------------
 struct GemmJob {
     TileMat A, B, C;

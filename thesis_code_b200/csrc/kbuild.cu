@@ -94,94 +94,145 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const double* __restrict
     if (tid == 0) { stats[k] = m; stats[d + k] = sqrt(red[0] / (double)N); }
 }
 
+constexpr int kTmaMaxD = 16;   // input dimensions up to this are staged with TMA bulk copies (all five BASELINE configs)
+
+__device__ __forceinline__ uint32_t kb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // One CTA (256 threads) per output tile.  Rows come from (Xa, asq) tile ti, columns from (Xb, bsq) tile tj.
+//  * staging: the 128 x d block of input rows of a tile is contiguous in the row-major inputs, so for d <= kTmaMaxD one
+//    elected thread fetches each operand's block with ONE 1-D TMA bulk copy (cp.async.bulk, mbarrier complete_tx) and the
+//    CTA re-lays it k-major in shared memory; wider inputs are gathered with coalesced loads in chunks of kMaxD columns.
+//  * Gram product: k-major operands make the two columns a thread owns adjacent -> one 128-bit shared load feeds two FMAs,
+//    the row operand is a conflict-free 64-bit load (8 distinct rows per warp).
+//  * epilogue: r^2 -> sqrt -> (/ lengthscale) -> K_of_r, compiled per kernel (KID) so no per-element dispatch.
 // Thread mapping = the DMMA accumulator fragment pattern: lane (g = lane>>2, t = lane&3) of warp w owns, for each
 // of its 2 row blocks and 16 column chunks, the pair (r, c..c+1) -> one 16 B store; a warp stores 512 contiguous B.
-template <bool kSymmetric, bool kFused>
+template <bool kSymmetric, bool kFused, int KID>
 __device__ __forceinline__ void build_tile(double* __restrict__ out, const double* __restrict__ Xa,
                                            const double* __restrict__ asq, int64_t Na, int ti,
                                            const double* __restrict__ Xb, const double* __restrict__ bsq,
-                                           int64_t Nb, int tj, int d, int kernel_id, double variance,
-                                           double rdiv, double diag_add, double* sm,
+                                           int64_t Nb, int tj, int d, double variance,
+                                           double rdiv, double diag_add, double* sm, int pass,
                                            const double* __restrict__ alpha_tile, int O, int64_t alpha_stride,
                                            double* __restrict__ red, double* __restrict__ vec_row0, int64_t vec_stride,
                                            int vec_rows) {
     // the input dimension is processed in chunks of at most kMaxD columns (any d is supported)
     const int dcap = d < kMaxD ? d : kMaxD;
-    const int dp = dcap | 1;
     const int nchunks = (d + kMaxD - 1) / kMaxD;
-    double* sa = sm;                      // [128][dp]
-    double* sb = sa + GPX_TILE * dp;      // [128][dp]
-    double* sasq = sb + GPX_TILE * dp;    // [128]
-    double* sbsq = sasq + GPX_TILE;       // [128]
+    double* sat = sm;                          // [dcap][128]  k-major row operand
+    double* sbt = sat + GPX_TILE * dcap;       // [dcap][128]  k-major column operand
+    double* sasq = sbt + GPX_TILE * dcap;      // [128]
+    double* sbsq = sasq + GPX_TILE;            // [128]
+    double* stage = sbsq + GPX_TILE;           // [2][128][d]  TMA landing zone (d <= kTmaMaxD only), then the mbarrier
     const int tid = threadIdx.x;
-    if (tid < GPX_TILE) {
+    const bool use_tma = d <= kTmaMaxD;
+    if (use_tma) {
+        uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 2 * GPX_TILE * kTmaMaxD);
+        const uint32_t bytes = (uint32_t)(GPX_TILE * d * sizeof(double));
+        if (tid == 0) {
+            if (pass == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(kb_smem_u32(bar)) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kb_smem_u32(bar)), "r"(2 * bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(kb_smem_u32(stage)),
+                         "l"(Xa + (int64_t)ti * GPX_TILE * d), "r"(bytes), "r"(kb_smem_u32(bar)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(kb_smem_u32(stage + GPX_TILE * d)),
+                         "l"(Xb + (int64_t)tj * GPX_TILE * d), "r"(bytes), "r"(kb_smem_u32(bar)) : "memory");
+        }
+        if (tid < GPX_TILE) {
+            sasq[tid] = asq[(int64_t)ti * GPX_TILE + tid];
+            sbsq[tid] = bsq[(int64_t)tj * GPX_TILE + tid];
+        }
+        __syncthreads();   // the barrier is initialised before anybody polls it
+        {
+            uint32_t ok = 0;
+            const uint32_t parity = (uint32_t)(pass & 1);
+            while (!ok) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(ok) : "r"(kb_smem_u32(bar)), "r"(parity) : "memory");
+            }
+        }
+        for (int e = tid; e < GPX_TILE * d; e += blockDim.x) {   // [row][d] -> [k][row]
+            const int rr = e / d, k = e - rr * d;
+            sat[k * GPX_TILE + rr] = stage[e];
+            sbt[k * GPX_TILE + rr] = stage[GPX_TILE * d + e];
+        }
+        __syncthreads();
+    } else if (tid < GPX_TILE) {
         sasq[tid] = asq[(int64_t)ti * GPX_TILE + tid];
         sbsq[tid] = bsq[(int64_t)tj * GPX_TILE + tid];
     }
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const bool dtile = kSymmetric && ti == tj;
+    const int64_t cv = Nb - (int64_t)tj * GPX_TILE;
+    const int ncv = cv > GPX_TILE ? GPX_TILE : (int)(cv < 0 ? 0 : cv);   // valid columns of this tile
 #pragma unroll
     for (int rb = 0; rb < 2; rb++) {
         const int r = warp * 16 + rb * 8 + g;
-        const int64_t gi = (int64_t)ti * GPX_TILE + r;
-        double dot[16][2];
-#pragma unroll
-        for (int kc = 0; kc < 16; kc++) { dot[kc][0] = 0.0; dot[kc][1] = 0.0; }
-        for (int ci = 0; ci < nchunks; ci++) {
-            const int d0 = ci * kMaxD, dc = (d - d0 < kMaxD) ? (d - d0) : kMaxD;
-            if (rb == 0 || nchunks > 1) {   // a single chunk stays resident for the second row block
-                __syncthreads();
-                for (int e = tid; e < GPX_TILE * dc; e += blockDim.x) {
-                    int rr = e / dc, k = e - rr * dc;
-                    sa[rr * dp + k] = Xa[((int64_t)ti * GPX_TILE + rr) * d + d0 + k];
-                    sb[rr * dp + k] = Xb[((int64_t)tj * GPX_TILE + rr) * d + d0 + k];
-                }
-                __syncthreads();
-            }
-            for (int k = 0; k < dc; k++) {
-                double a = sa[r * dp + k];
-#pragma unroll
-                for (int kc = 0; kc < 16; kc++) {
-                    int c = kc * 8 + 2 * t;
-                    dot[kc][0] = fma(a, sb[c * dp + k], dot[kc][0]);
-                    dot[kc][1] = fma(a, sb[(c + 1) * dp + k], dot[kc][1]);
-                }
-            }
-        }
-        const double ra = sasq[r];
+        const bool row_ok = (int64_t)ti * GPX_TILE + r < Na;
         double msum[kMaxFusedO];
 #pragma unroll
         for (int o = 0; o < kMaxFusedO; o++) msum[o] = 0.0;
+        // the 16 column chunks are taken in two halves of 8 (32 accumulators live instead of 64: no spills at 128 registers)
+#pragma unroll 1
+        for (int hf = 0; hf < 2; hf++) {
+            double dot[8][2];
 #pragma unroll
-        for (int kc = 0; kc < 16; kc++) {
-            double v[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                int c = kc * 8 + 2 * t + h;
-                int64_t gj = (int64_t)tj * GPX_TILE + c;
-                double r2 = -2.0 * dot[kc][h] + (ra + sbsq[c]);
-                r2 = fmax(r2, 0.0);
-                double kv;
-                if (kSymmetric) {
-                    if (gi == gj) r2 = 0.0;
-                    kv = gpx_k_of_r(kernel_id, variance, gpx_scaled_r(r2, rdiv));
-                    if (gi == gj) kv += diag_add;
-                    if (gi >= Na || gj >= Nb) kv = (gi == gj) ? 1.0 : 0.0;  // identity padding
-                } else {
-                    kv = gpx_k_of_r(kernel_id, variance, gpx_scaled_r(r2, rdiv));
-                    if (gi >= Na || gj >= Nb) kv = 0.0;
+            for (int q = 0; q < 8; q++) { dot[q][0] = 0.0; dot[q][1] = 0.0; }
+            for (int ci = 0; ci < nchunks; ci++) {
+                const int d0 = ci * kMaxD, dc = (d - d0 < kMaxD) ? (d - d0) : kMaxD;
+                if (!use_tma && ((rb == 0 && hf == 0) || nchunks > 1)) {   // a single chunk stays resident for all four passes
+                    __syncthreads();
+                    for (int e = tid; e < GPX_TILE * dc; e += blockDim.x) {
+                        const int rr = e / dc, k = e - rr * dc;
+                        sat[k * GPX_TILE + rr] = Xa[((int64_t)ti * GPX_TILE + rr) * d + d0 + k];
+                        sbt[k * GPX_TILE + rr] = Xb[((int64_t)tj * GPX_TILE + rr) * d + d0 + k];
+                    }
+                    __syncthreads();
                 }
-                v[h] = kv;
+                for (int k = 0; k < dc; k++) {
+                    const double a = sat[k * GPX_TILE + r];
+                    const double2* bp = reinterpret_cast<const double2*>(sbt + k * GPX_TILE + hf * 64 + 2 * t);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const double2 bv = bp[q * 4];
+                        dot[q][0] = fma(a, bv.x, dot[q][0]);
+                        dot[q][1] = fma(a, bv.y, dot[q][1]);
+                    }
+                }
             }
-            if (out) *reinterpret_cast<double2*>(out + kc * 1024 + r * 8 + 2 * t) = make_double2(v[0], v[1]);
-            if (kFused && vec_row0 && r < vec_rows)   // latency path: k(x*_r, X) as right-hand-side vectors for the GEMV-style solve
-                *reinterpret_cast<double2*>(vec_row0 + (int64_t)r * vec_stride + kc * 8 + 2 * t) = make_double2(v[0], v[1]);
-            if (kFused && alpha_tile) {               // fused predictive-mean partial sums: sum_c K[r][c] alpha[o][c] over this thread's columns
-                const int c = kc * 8 + 2 * t;
-                for (int o = 0; o < O && o < kMaxFusedO; o++) {
-                    const double* al = alpha_tile + (int64_t)o * alpha_stride;
-                    msum[o] = fma(v[0], al[c], msum[o]);
-                    msum[o] = fma(v[1], al[c + 1], msum[o]);
+            const double ra = sasq[r];   // (written before the block-wide barriers of the staging above)
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int kc = hf * 8 + q;
+                double v[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int c = kc * 8 + 2 * t + h;
+                    double r2 = -2.0 * dot[q][h] + (ra + sbsq[c]);
+                    r2 = fmax(r2, 0.0);
+                    const bool diag = dtile && r == c;
+                    if (kSymmetric && diag) r2 = 0.0;
+                    double kv = gpx_k_of_r_t<KID>(variance, gpx_scaled_r(r2, rdiv));
+                    if (kSymmetric) {
+                        if (diag) kv += diag_add;
+                        if (!row_ok || c >= ncv) kv = diag ? 1.0 : 0.0;  // identity padding
+                    } else {
+                        if (!row_ok || c >= ncv) kv = 0.0;
+                    }
+                    v[h] = kv;
+                }
+                if (out) *reinterpret_cast<double2*>(out + kc * 1024 + r * 8 + 2 * t) = make_double2(v[0], v[1]);
+                if (kFused && vec_row0 && r < vec_rows)   // latency path: k(x*_r, X) as right-hand-side vectors for the GEMV-style solve
+                    *reinterpret_cast<double2*>(vec_row0 + (int64_t)r * vec_stride + kc * 8 + 2 * t) = make_double2(v[0], v[1]);
+                if (kFused && alpha_tile) {               // fused predictive-mean partial sums over this thread's columns
+                    const int c = kc * 8 + 2 * t;
+                    for (int o = 0; o < O && o < kMaxFusedO; o++) {
+                        const double* al = alpha_tile + (int64_t)o * alpha_stride;
+                        msum[o] = fma(v[0], al[c], msum[o]);
+                        msum[o] = fma(v[1], al[c + 1], msum[o]);
+                    }
                 }
             }
         }
@@ -192,25 +243,27 @@ __device__ __forceinline__ void build_tile(double* __restrict__ out, const doubl
 }
 
 // K(X,X) + diag_add I into the packed lower factor storage: grid (nt, number of tile columns handled here).
+template <int KID>
 __global__ void __launch_bounds__(256, GPX_KBUILD_MINBLOCKS) kbuild_lower_kernel(TileMat L, int nt, int jfirst, int jstep, int i_first,
                                                            const double* __restrict__ Xs,
                                                            const double* __restrict__ xsq, int64_t N, int d,
-                                                           int kernel_id, double variance, double rdiv, double diag_add) {
+                                                           double variance, double rdiv, double diag_add) {
     extern __shared__ __align__(16) double sm[];
     const int J = jfirst + blockIdx.y * jstep;
     const int I = i_first + blockIdx.x;
     if (J >= nt || I >= nt || I < J) return;
-    build_tile<true, false>(tile_ptr(L, I, J), Xs, xsq, N, I, Xs, xsq, N, J, d, kernel_id, variance, rdiv, diag_add, sm, nullptr, 0, 0,
-                     nullptr, nullptr, 0, 0);
+    build_tile<true, false, KID>(tile_ptr(L, I, J), Xs, xsq, N, I, Xs, xsq, N, J, d, variance, rdiv, diag_add, sm, 0, nullptr, 0, 0,
+                                 nullptr, nullptr, 0, 0);
 }
 
 // K(X*, X) tiles (rows = test points, cols = training points) into Tt (if Tt.base != null) and the fused
 // predictive-mean partial sums  mean_partial[J][n][o] = sum_{j in tile J} K(x*_n, x_j) alpha[o][j].
 // grid (nbt, nt).
+template <int KID>
 __global__ void __launch_bounds__(256, 2) kcross_kernel(TileMat Tt, int nbt, int nt, const double* __restrict__ Xt,
                                                      const double* __restrict__ xtsq, int64_t Nt_valid,
                                                      const double* __restrict__ Xs, const double* __restrict__ xsq,
-                                                     int64_t N, int d, int kernel_id, double variance, double rdiv,
+                                                     int64_t N, int d, double variance, double rdiv,
                                                      const double* __restrict__ alpha, int O, int64_t Np,
                                                      double* __restrict__ mean_partial, double* __restrict__ vec_out,
                                                      int vec_rows) {
@@ -225,7 +278,7 @@ __global__ void __launch_bounds__(256, 2) kcross_kernel(TileMat Tt, int nbt, int
         const int Oc = mean_partial ? ((O - o0 < kMaxFusedO) ? (O - o0) : kMaxFusedO) : 0;
         const bool first = (o0 == 0);
         if (!first) __syncthreads();
-        build_tile<false, true>(first ? out : nullptr, Xt, xtsq, Nt_valid, n, Xs, xsq, N, J, d, kernel_id, variance, rdiv, 0.0, sm,
+        build_tile<false, true, KID>(first ? out : nullptr, Xt, xtsq, Nt_valid, n, Xs, xsq, N, J, d, variance, rdiv, 0.0, sm, o0 / kMaxFusedO,
                           mean_partial ? alpha + (int64_t)o0 * Np + (int64_t)J * GPX_TILE : nullptr, Oc, Np, red,
                           (first && vec_out && n == 0) ? vec_out + (int64_t)J * GPX_TILE : nullptr, Np, vec_rows);
         if (!mean_partial) return;
@@ -319,8 +372,10 @@ __global__ void detile_kernel(TileMat M, int lower, int64_t rows, int64_t cols, 
 }  // namespace
 
 static size_t kb_smem(int d) {
-    int dc = d < kMaxD ? d : kMaxD;
-    return (size_t)(2 * GPX_TILE * (dc | 1) + 2 * GPX_TILE) * sizeof(double);
+    const int dc = d < kMaxD ? d : kMaxD;
+    size_t doubles = (size_t)2 * GPX_TILE * dc + 2 * GPX_TILE;                 // k-major operands + squared norms
+    if (d <= kTmaMaxD) doubles += (size_t)2 * GPX_TILE * kTmaMaxD + 2;         // TMA landing zone + mbarrier
+    return doubles * sizeof(double);
 }
 
 int gpx_kbuild_max_d() { return 1 << 20; }   // any input dimension (processed in chunks of kMaxD)
@@ -328,12 +383,27 @@ int gpx_grad_max_d() { return kMaxD; }       // the gradient kernel keeps one pa
 
 static void gpx_grad_init_attr();   // defined after the gradient kernel below
 
+template <int KID>
+static void kb_set_attr(int bytes) {
+    cudaFuncSetAttribute(kbuild_lower_kernel<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(kcross_kernel<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 // per device (function attributes are per device): called from gpx_create after cudaSetDevice
 void gpx_kbuild_init() {
     gpx_grad_init_attr();
-    size_t s = kb_smem(kMaxD);
-    cudaFuncSetAttribute(kbuild_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s);
-    cudaFuncSetAttribute(kcross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s);
+    size_t a = kb_smem(kMaxD), b = kb_smem(kTmaMaxD);
+    const int s = (int)(a > b ? a : b);
+    kb_set_attr<0>(s); kb_set_attr<1>(s); kb_set_attr<2>(s); kb_set_attr<3>(s);
+}
+
+static void kb_launch_lower(int kernel_id, dim3 grid, size_t smem, cudaStream_t st, TileMat L, int nt, int jfirst, int jstep, int i_first,
+                            const double* Xs, const double* xsq, int64_t N, int d, double variance, double rdiv, double diag_add) {
+    switch (kernel_id) {
+#define GPX_KLOWER(K) case K: kbuild_lower_kernel<K><<<grid, 256, smem, st>>>(L, nt, jfirst, jstep, i_first, Xs, xsq, N, d, variance, rdiv, diag_add); break;
+        GPX_KLOWER(0) GPX_KLOWER(1) GPX_KLOWER(2) GPX_KLOWER(3)
+#undef GPX_KLOWER
+    }
 }
 
 void gpx_launch_prep_x(const double* X, int64_t N, int64_t Np, int d, const double* ls, int ard, const double* shift,
@@ -352,8 +422,7 @@ void gpx_launch_kbuild_lower(TileMat L, int nt, int jfirst, int jstep, int ncols
                              double diag_add, cudaStream_t st) {
     if (ncols <= 0) return;
     dim3 grid(nt, ncols);
-    kbuild_lower_kernel<<<grid, 256, kb_smem(d), st>>>(L, nt, jfirst, jstep, 0, Xs, xsq, N, d, kernel_id, variance, rdiv,
-                                                       diag_add);
+    kb_launch_lower(kernel_id, grid, kb_smem(d), st, L, nt, jfirst, jstep, 0, Xs, xsq, N, d, variance, rdiv, diag_add);
 }
 
 // the tile rows [i_first, nt) of K(X,X) + diag_add I only (gpx_append: rows of new observations)
@@ -361,8 +430,7 @@ void gpx_launch_kbuild_rows(TileMat L, int nt, int i_first, const double* Xs, co
                             int kernel_id, double variance, double rdiv, double diag_add, cudaStream_t st) {
     if (i_first >= nt) return;
     dim3 grid(nt - i_first, nt);
-    kbuild_lower_kernel<<<grid, 256, kb_smem(d), st>>>(L, nt, 0, 1, i_first, Xs, xsq, N, d, kernel_id, variance, rdiv,
-                                                       diag_add);
+    kb_launch_lower(kernel_id, grid, kb_smem(d), st, L, nt, 0, 1, i_first, Xs, xsq, N, d, variance, rdiv, diag_add);
 }
 
 void gpx_launch_kcross(TileMat Tt, int nb, int nbt_layout, int nt, const double* Xt, const double* xtsq,
@@ -370,8 +438,12 @@ void gpx_launch_kcross(TileMat Tt, int nb, int nbt_layout, int nt, const double*
                        double variance, double rdiv, const double* alpha, int O, int64_t Np, double* mean_partial,
                        cudaStream_t st, double* vec_out, int vec_rows) {
     dim3 grid(nb, nt);
-    kcross_kernel<<<grid, 256, kb_smem(d), st>>>(Tt, nbt_layout, nt, Xt, xtsq, Nt_valid, Xs, xsq, N, d, kernel_id, variance,
-                                                 rdiv, alpha, O, Np, mean_partial, vec_out, vec_rows);
+    switch (kernel_id) {
+#define GPX_KCROSS(K) case K: kcross_kernel<K><<<grid, 256, kb_smem(d), st>>>(Tt, nbt_layout, nt, Xt, xtsq, Nt_valid, Xs, xsq, N, d, variance, \
+                                                                          rdiv, alpha, O, Np, mean_partial, vec_out, vec_rows); break;
+        GPX_KCROSS(0) GPX_KCROSS(1) GPX_KCROSS(2) GPX_KCROSS(3)
+#undef GPX_KCROSS
+    }
 }
 
 void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, double mean_const, const double* ystats,
