@@ -366,7 +366,7 @@ void gpx_destroy(gpx_t* h) {
                      &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->gbuf[0], &h->gbuf[1], &h->cache,
                      &h->ucoloff, &h->Tt,
                      &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar, &h->sp, &h->xstats, &h->ystats, &h->var_partial, &h->minv, &h->minv_coloff,
-                     &h->ywork, &h->ywork_coloff};
+                     &h->ywork, &h->ywork_coloff, &h->zkeep};
     for (DevBuf* b : all) release(h, *b);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->pin) cudaFreeHost(h->pin);
@@ -488,6 +488,7 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     const int64_t Np = (int64_t)cap_nt * GPX_TILE;
     h->cap_nt = cap_nt;
     h->gen++;   // invalidates captured predict graphs
+    h->minv_valid = 0;
     h->N = N; h->Np = Np; h->nt = nt; h->d = d; h->O = O; h->kernel_id = kernel_id; h->n_ls = n_ls;
     h->variance = variance; h->noise = noise; h->jitter = jitter; h->mean_const = mean_const;
     h->ard = ard ? 1 : 0;
@@ -637,7 +638,12 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     rc = cholesky(h);
     phase_end(h, GPX_PHASE_CHOLESKY);
 
-    // alpha: backward substitution
+    // alpha: backward substitution (it consumes z in work2: keep a copy for gpx_append's incremental forward pass)
+    h->zkeep_valid = false;
+    if (!rc && G == 1 && ensure(h, h->zkeep, (size_t)Np * O * 8) == 0) {
+        GPX_CUDA(h, cudaMemcpyAsync(h->zkeep.p, h->work2.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, h->st));
+        h->zkeep_valid = true;
+    }
     if (!rc) {
         phase_begin(h, GPX_PHASE_SOLVE);
         rc = backward_solve(h);
@@ -718,18 +724,18 @@ int gpx_lml(gpx_t* h, double* lml, double* logdet, double* quad) {
 
 // in-panel part of the blocked solve  X <- X L^-T  for the tile rows [0, nb) of X and the tile columns [p0, p1): per
 // column a TRSM against the inverted diagonal tile, then a rank-128 update of the panel's remaining columns
-static void trsm_inner_stepwise(gpx_t* h, TileMat X, int nb, TileMat P, int p0, int p1) {
+void trsm_inner_stepwise(gpx_t* h, TileMat X, int nb, TileMat P, int p0, int p1, int i0) {
     TileMat Li = linvmat(h);
     for (int k = p0; k < p1; k++) {
         GemmJob t{};
         t.A = X; t.B = Li; t.C = X;
-        t.tri = 0; t.i0 = 0; t.i1 = nb; t.ncols = 1; t.jbase = k; t.jW = GPX_JW_CONTIG; t.jstride = 0;
+        t.tri = 0; t.i0 = i0; t.i1 = nb; t.ncols = 1; t.jbase = k; t.jW = GPX_JW_CONTIG; t.jstride = 0;
         t.k0 = k; t.k1 = k + 1; t.bdiag = 1; t.overwrite = 1;
         gemm(h, t, h->st);
         if (k + 1 < p1) {
             GemmJob u{};
             u.A = X; u.B = P; u.C = X;
-            u.tri = 0; u.i0 = 0; u.i1 = nb; u.ncols = p1 - (k + 1); u.jbase = k + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+            u.tri = 0; u.i0 = i0; u.i1 = nb; u.ncols = p1 - (k + 1); u.jbase = k + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
             u.k0 = k; u.k1 = k + 1; u.bdiag = 0; u.overwrite = 0;
             gemm(h, u, h->st);
         }
@@ -742,33 +748,42 @@ static void trsm_inner_stepwise(gpx_t* h, TileMat X, int nb, TileMat P, int p0, 
 // pay a launch ramp and tail each): at BASELINE config C4 the in-panel steps are 3.5 % of the variance solve's flops but
 // cost ~6 % of its time.  Built lazily by the first large predict after a fit: Y = M_p^T from the step-wise solve applied
 // to an identity block, then transposed tile by tile (the tile GEMM computes A B^T only).
-static int ensure_panel_inverse(gpx_t* h) {
-    if (h->minv_gen == h->gen && h->minv.p) return 0;
-    const int nt = h->nt, W = h->W, np = h->npanels;
-    std::vector<int64_t> moff(nt), yoff(nt);
-    int64_t tiles = 0;
-    for (int c = 0; c < nt; c++) {
-        const int p1 = panel_end(h, c / W);
-        moff[c] = tiles * GPX_TILE_ELEMS;
-        tiles += p1 - c;
-        yoff[c] = (int64_t)(c % W) * W * GPX_TILE_ELEMS;
+// Built lazily and incrementally: panels [minv_valid, upto_panel) are (re)computed; gpx_append only invalidates the panels it
+// touches.
+int ensure_panel_inverse(gpx_t* h, int upto_panel) {
+    const int W = h->W, cap = h->cap_nt;
+    if (upto_panel > h->npanels) upto_panel = h->npanels;
+    // layout by CAPACITY (cap_nt), so that gpx_append can keep the blocks of untouched panels: column c holds the tiles
+    // (c .. end of its panel) and the offsets do not move when nt grows inside the capacity
+    if (!h->minv.p || h->minv_layout_cap != cap || h->minv_layout_w != W) {
+        std::vector<int64_t> moff(cap), yoff(cap);
+        int64_t tiles = 0;
+        for (int c = 0; c < cap; c++) {
+            int p1 = (c / W + 1) * W;
+            if (p1 > cap) p1 = cap;
+            moff[c] = tiles * GPX_TILE_ELEMS;
+            tiles += p1 - c;
+            yoff[c] = (int64_t)(c % W) * W * GPX_TILE_ELEMS;
+        }
+        int rc;
+        if ((rc = ensure(h, h->minv, (size_t)tiles * GPX_TILE_BYTES)) || (rc = ensure(h, h->minv_coloff, (size_t)cap * 8)) ||
+            (rc = ensure(h, h->ywork, (size_t)W * W * GPX_TILE_BYTES)) || (rc = ensure(h, h->ywork_coloff, (size_t)cap * 8))) return rc;
+        GPX_CUDA(h, cudaMemcpyAsync(h->minv_coloff.p, moff.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, h->st));
+        GPX_CUDA(h, cudaMemcpyAsync(h->ywork_coloff.p, yoff.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, h->st));
+        GPX_CUDA(h, cudaStreamSynchronize(h->st));   // moff / yoff are host temporaries
+        h->minv_layout_cap = cap; h->minv_layout_w = W;
+        h->minv_valid = 0;
     }
-    int rc;
-    if ((rc = ensure(h, h->minv, (size_t)tiles * GPX_TILE_BYTES)) || (rc = ensure(h, h->minv_coloff, (size_t)nt * 8)) ||
-        (rc = ensure(h, h->ywork, (size_t)W * W * GPX_TILE_BYTES)) || (rc = ensure(h, h->ywork_coloff, (size_t)nt * 8))) return rc;
-    GPX_CUDA(h, cudaMemcpyAsync(h->minv_coloff.p, moff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
-    GPX_CUDA(h, cudaMemcpyAsync(h->ywork_coloff.p, yoff.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st));
-    GPX_CUDA(h, cudaStreamSynchronize(h->st));   // moff / yoff are host temporaries
     TileMat Y{ptr<double>(h->ywork), ptr<int64_t>(h->ywork_coloff), 0};
     TileMat M{ptr<double>(h->minv), ptr<int64_t>(h->minv_coloff), 1};
-    for (int p = 0; p < np; p++) {
+    for (int p = h->minv_valid; p < upto_panel; p++) {
         const int p0 = panel_begin(h, p), p1 = panel_end(h, p);
         gpx_launch_identity_block(Y, p1 - p0, p0, h->st);
         trsm_inner_stepwise(h, Y, p1 - p0, lmat(h), p0, p1);
         gpx_launch_transpose_block(Y, M, p0, p1 - p0, h->st);
         h->launches += 2;
     }
-    h->minv_gen = h->gen;
+    if (upto_panel > h->minv_valid) h->minv_valid = upto_panel;
     return 0;
 }
 
@@ -909,7 +924,7 @@ int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* va
     // in-panel solve through the inverted diagonal blocks: pays when there are enough test tiles to amortise building them
     h->minv_active = 0;
     if (var && G == 1 && h->W >= 2 && (h->panel_inverse == 1 || (h->panel_inverse < 0 && total_tiles >= 64))) {
-        if ((rc = ensure_panel_inverse(h))) return rc;
+        if ((rc = ensure_panel_inverse(h, h->npanels))) return rc;
         h->minv_active = 1;
     }
 

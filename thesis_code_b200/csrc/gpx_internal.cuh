@@ -97,7 +97,10 @@ struct gpx_handle {
     int panel_inverse = -1;               // option "panel_inverse": in-panel variance solve through inverted diagonal blocks
                                           // (-1 auto: predicts with >= 64 test tiles on one GPU; 0 off; 1 on)
     int minv_active = 0;                  // set by gpx_predict around its batch loop
-    uint64_t minv_gen = 0;                // fit generation the inverted blocks belong to
+    DevBuf zkeep;                         // z = L^-1 (Y - m) of the last fit / append (the backward pass consumes work2)
+    bool zkeep_valid = false;
+    int minv_valid = 0;                   // leading panels whose inverted diagonal blocks are up to date
+    int minv_layout_cap = -1, minv_layout_w = -1;
     DevBuf minv, minv_coloff, ywork, ywork_coloff;
     int trace = 0;                        // 1: per-panel timeline events during the Cholesky (gpx_trace)
     std::vector<cudaEvent_t> tev;         // 6 per panel + 1 base, timing enabled
@@ -344,6 +347,9 @@ inline int ensure_panel_events(gpx_t* h, int npanels) {
 void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows = false);
 int var_trsm(gpx_t* h, TileMat Tt, int nb);
 int backward_solve(gpx_t* h);
+int ensure_panel_inverse(gpx_t* h, int upto_panel);
+// step-wise in-panel solve of the tile rows [i0, nb) of X against the columns [p0, p1) of P
+void trsm_inner_stepwise(gpx_t* h, TileMat X, int nb, TileMat P, int p0, int p1, int i0 = 0);   // inverted W x W-tile diagonal blocks of the panels [0, upto_panel)
 int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int var_cols, int include_noise,
                       int mem);
 void gpx_launch_kbuild_rows(TileMat L, int nt, int i_first, const double* Xs, const double* xsq, int64_t N, int d,

@@ -36,6 +36,58 @@ __global__ void __launch_bounds__(256) vec_var_kernel(const double* __restrict__
     }
 }
 
+// Incremental forward substitution of gpx_append: partial[(i * S + s)][o][r] = sum over the tile columns J of split s
+// (J < jend) of (L(i0 + i, J) z_o[J])[r]  -- the new tile rows against the z the fit left behind.  grid (rows, S).
+constexpr int kRowRhs = 8;
+__global__ void __launch_bounds__(256) row_gemv_partial_kernel(TileMat L, int i0, int jend, int S, const double* __restrict__ z,
+                                                               int64_t Np, int O, double* __restrict__ partial) {
+    __shared__ double sz[kRowRhs][GPX_TILE], scratch[kRowRhs][GPX_TILE];
+    const int i = blockIdx.x, sidx = blockIdx.y, tid = threadIdx.x, r = tid & 127, half = tid >> 7;
+    const int J0 = (int)((long long)jend * sidx / S), J1 = (int)((long long)jend * (sidx + 1) / S);
+    double acc[kRowRhs];
+#pragma unroll
+    for (int o = 0; o < kRowRhs; o++) acc[o] = 0.0;
+    for (int J = J0; J < J1; J++) {
+        __syncthreads();
+        for (int e = tid; e < O * GPX_TILE; e += 256) sz[e >> 7][e & 127] = z[(int64_t)(e >> 7) * Np + (int64_t)J * GPX_TILE + (e & 127)];
+        __syncthreads();
+        const double* tp = tile_ptr(L, i0 + i, J);
+#pragma unroll
+        for (int kc = 0; kc < 8; kc++) {
+            const int ch = half * 8 + kc;
+            const double2* p = reinterpret_cast<const double2*>(tp + ch * 1024 + r * 8);
+            const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+#pragma unroll
+            for (int o = 0; o < kRowRhs; o++) {
+                if (o < O) {
+                    const double* x = &sz[o][ch * 8];
+                    double a = acc[o];
+                    a = fma(v0.x, x[0], a); a = fma(v0.y, x[1], a); a = fma(v1.x, x[2], a); a = fma(v1.y, x[3], a);
+                    a = fma(v2.x, x[4], a); a = fma(v2.y, x[5], a); a = fma(v3.x, x[6], a); a = fma(v3.y, x[7], a);
+                    acc[o] = a;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < kRowRhs; o++) if (o < O && half == 1) scratch[o][r] = acc[o];
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < kRowRhs; o++)
+        if (o < O && half == 0) partial[(((int64_t)i * S + sidx) * O + o) * GPX_TILE + r] = acc[o] + scratch[o][r];
+}
+
+// b[o][(i0 + i) * 128 + r] -= sum_s partial[(i * S + s)][o][r]   (fixed order)
+__global__ void row_gemv_apply_kernel(const double* __restrict__ partial, int rows, int S, int O, int i0, int64_t Np,
+                                      double* __restrict__ b) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)rows * O * GPX_TILE) return;
+    const int r = (int)(e & 127), o = (int)((e >> 7) % O), i = (int)((e >> 7) / O);
+    double s = 0.0;
+    for (int k = 0; k < S; k++) s += partial[(((int64_t)i * S + k) * O + o) * GPX_TILE + r];
+    b[(int64_t)o * Np + (int64_t)(i0 + i) * GPX_TILE + r] -= s;
+}
+
 // v[i] = fixed pseudo-random value in (-1, 1) for i < N, 0 for the padding (splitmix64 of the index)
 __global__ void fill_random_kernel(double* __restrict__ v, int64_t N, int64_t Np) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,6 +297,7 @@ int relayout(gpx_t* h, int new_cap) {
     const int64_t elems = packed_offsets(new_cap, noff);
     for (int c = 0; c < new_cap; c++) lc[c] = (int64_t)c * GPX_TILE_ELEMS;
     DevBuf nL, nlinv, nXs, nxsq, nres, nw1, nw2, nal, ncoloff, nlcoloff;
+    h->zkeep_valid = false;   // the kept forward solution is simply recomputed by the next append (full forward pass)
     int rc;
     auto bail = [&](int code) { for (DevBuf* b : {&nL, &nlinv, &nXs, &nxsq, &nres, &nw1, &nw2, &nal, &ncoloff, &nlcoloff}) release(h, *b); return code; };
     if ((rc = ensure(h, nL, (size_t)elems * 8)) || (rc = ensure(h, nlinv, (size_t)new_cap * GPX_TILE_BYTES)) ||
@@ -450,22 +503,24 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     h->launches++;
     // 2. solve them against the resident factor: L(R, J) = (K(R, J) - sum_{k<J} L(R,k) L(J,k)^T) Linv_J^T for J < t0, and
     //    subtract their outer product from the new diagonal block -- panel by panel, exactly the predictive-variance solve
-    TileMat L = lmat(h), Li = linvmat(h);
+    //    Panels that lie entirely below the new rows go through their inverted diagonal block (one row-wise GEMM instead
+    //    of 2 W - 1 single-tile launches: an append is latency-bound); the blocks are cached across appends, only the panels
+    //    the append touches are invalidated.
+    TileMat L = lmat(h);
+    const int full_panels = t0 / W;
+    if (h->minv_valid > full_panels) h->minv_valid = full_panels;
+    if (full_panels > 0 && (rc = ensure_panel_inverse(h, full_panels))) { release(h, stageY); return rc; }
+    TileMat Mi{ptr<double>(h->minv), ptr<int64_t>(h->minv_coloff), 1};
     for (int c0 = 0; c0 < t0; c0 += W) {
         const int c1 = c0 + W < t0 ? c0 + W : t0;
-        for (int c = c0; c < c1; c++) {
+        if (c1 - c0 == W && c0 / W < full_panels) {
             GemmJob t{};
-            t.A = L; t.B = Li; t.C = L;
-            t.tri = 0; t.i0 = t0; t.i1 = nt1; t.ncols = 1; t.jbase = c; t.jW = GPX_JW_CONTIG; t.jstride = 0;
-            t.k0 = c; t.k1 = c + 1; t.bdiag = 1; t.overwrite = 1;
+            t.A = L; t.B = Mi; t.C = L;
+            t.tri = 0; t.i0 = t0; t.i1 = nt1; t.ncols = W; t.jbase = c0; t.jW = GPX_JW_CONTIG; t.jstride = 0;
+            t.k0 = c0; t.k1 = c1; t.bdiag = 0; t.overwrite = 1; t.rowwise = 1;
             gemm(h, t, st);
-            if (c + 1 < c1) {
-                GemmJob u{};
-                u.A = L; u.B = L; u.C = L;
-                u.tri = 0; u.i0 = t0; u.i1 = nt1; u.ncols = c1 - (c + 1); u.jbase = c + 1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
-                u.k0 = c; u.k1 = c + 1; u.bdiag = 0; u.overwrite = 0;
-                gemm(h, u, st);
-            }
+        } else {
+            trsm_inner_stepwise(h, L, nt1, L, c0, c1, t0);
         }
         if (c1 < t0) {
             GemmJob u{};
@@ -482,12 +537,30 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     }
     // 3. Cholesky of the Schur complement (the new diagonal block)
     factor_cols(h, t0, nt1, nt1, st);
-    // 4. alpha and the LML: two substitutions over the whole factor
+    // 4. alpha and the LML.  Forward substitution: only the new tile rows -- z of the old rows is what the fit (or the
+    //    previous append) left in zkeep; b_R = resid_R - sum_{J < t0} L(R, J) z_J by a split row GEMV, then the few steps inside
+    //    the new block.  (More than kRowRhs outputs, or no kept z: the plain full pass.)  Backward substitution: all of L.
     GPX_CUDA(h, cudaMemcpyAsync(h->work1.p, h->resid.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
-    for (int J = 0; J < nt1; J++) {
+    if ((rc = ensure(h, h->zkeep, (size_t)Np * O * 8))) { release(h, stageY); return rc; }
+    int jfirst = 0;
+    if (h->zkeep_valid && O <= kRowRhs && t0 > 0) {
+        const int rows = nt1 - t0;
+        int S = (2 * h->num_sms + rows - 1) / rows;
+        if (S > t0) S = t0;
+        if ((rc = ensure(h, h->var_partial, (size_t)rows * S * O * GPX_TILE * 8))) { release(h, stageY); return rc; }
+        GPX_CUDA(h, cudaMemcpyAsync(h->work2.p, h->zkeep.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
+        row_gemv_partial_kernel<<<dim3(rows, S), 256, 0, st>>>(L, t0, t0, S, ptr<double>(h->work2), Np, O, ptr<double>(h->var_partial));
+        row_gemv_apply_kernel<<<(int)(((int64_t)rows * O * GPX_TILE + 255) / 256), 256, 0, st>>>(ptr<double>(h->var_partial), rows, S, O, t0, Np,
+                                                                                              ptr<double>(h->work1));
+        h->launches += 2;
+        jfirst = t0;
+    }
+    for (int J = jfirst; J < nt1; J++) {
         gpx_launch_fwd_step(L, ptr<double>(h->linv), nt1, J, ptr<double>(h->work1), ptr<double>(h->work2), Np, O, 2 * h->num_sms, st);
         h->launches++;
     }
+    GPX_CUDA(h, cudaMemcpyAsync(h->zkeep.p, h->work2.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
+    h->zkeep_valid = true;
     rc = backward_solve(h);
     gpx_launch_lml(ptr<double>(h->linv), ptr<double>(h->alpha), ptr<double>(h->resid), (int64_t)nt1 * GPX_TILE, Np, O,
                    ptr<double>(h->scal), st);
