@@ -156,8 +156,8 @@ def test_committed_bench_lines_follow_the_contract():
     """The bench lines kept under profiles/ (produced by bench.py on B200s) carry every key the driver's contract names."""
     import glob
     import json
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_c*gpu.json")))
-    assert len(files) >= 3
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0[12]_bench_c*gpu.json")))
+    assert len(files) >= 6
     for f in files:
         line = json.loads(open(f).read().strip().splitlines()[-1])
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -172,3 +172,13 @@ def test_committed_bench_lines_follow_the_contract():
         assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 0
         assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"]) and line["cpu_baseline"]["kind"] == "port"
         assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if os.path.basename(f).startswith("r02"):
+            # round 2: every bench line carries a correctness check of the state it timed
+            c = line["check"]
+            assert c["solve_residual"] < 1e-9 and c["factor_residual"] < 1e-12 and c["var_min"] > 0
+            assert line["steps"] <= line["steps_requested"] and line["wall_s"] < line["budget_s"]
+            if line["n_gpus"] > 1:
+                assert c["lml_spread_over_ranks"] == 0.0
+            else:
+                g = c["golden_parity"]
+                assert max(g["mean_normwise"], g["var_normwise"], g["lml_rel"]) < g["gate"] == 1e-8

@@ -225,9 +225,14 @@ int cholesky(gpx_t* h) {
             double* slot = group_slot(p);
             const double* src = own ? ptr<double>(h->L) + h->h_coloff[p0] : slot;
             double* li = ptr<double>(h->linv) + (int64_t)p0 * GPX_TILE_ELEMS;
+            // Early panels go over the low-CTA communicator (an NCCL channel pins an SM for the whole transfer and the overlapped
+            // trailing update wants every SM).  Late in the factorisation the update of the owned columns is shorter than
+            // factor + broadcast of the next panel and the update stream waits for the panel (profiles/r02_trace_8gpu.txt: ~3 ms
+            // per panel around 75-85 % of the way at 8 GPUs, N = 200k): from there on the full-width communicator is used.
+            ncclComm_t bc = (100LL * p >= (long long)h->nccl_full_from_pct * np) ? h->comm : h->comm_lo;
             GPX_NCCL(h, nccl().GroupStart());
-            ncclResult_t r1 = nccl().Broadcast(src, slot, (size_t)panel_elems(h, p), ncclDouble, root, h->comm_lo, h->st_c);
-            ncclResult_t r2 = nccl().Broadcast(li, li, (size_t)(p1 - p0) * GPX_TILE_ELEMS, ncclDouble, root, h->comm_lo, h->st_c);
+            ncclResult_t r1 = nccl().Broadcast(src, slot, (size_t)panel_elems(h, p), ncclDouble, root, bc, h->st_c);
+            ncclResult_t r2 = nccl().Broadcast(li, li, (size_t)(p1 - p0) * GPX_TILE_ELEMS, ncclDouble, root, bc, h->st_c);
             GPX_NCCL(h, nccl().GroupEnd());
             GPX_NCCL(h, r1);
             GPX_NCCL(h, r2);
@@ -430,6 +435,7 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "cache_mb")) { h->cache_limit_mb = value; h->fitted = false; return 0; }
     if (!strcmp(name, "group_panels")) { if (value < 1 || value > 16) return fail(h, -1, "group_panels out of range"); h->group_panels = (int)value; h->fitted = false; return 0; }
     if (!strcmp(name, "nccl_lo_ctas")) { h->nccl_lo_ctas = (int)value; return 0; }  // takes effect at gpx_comm_init
+    if (!strcmp(name, "nccl_full_from_pct")) { h->nccl_full_from_pct = (int)value; return 0; }  // 100 = low-CTA communicator throughout
     if (!strcmp(name, "trace")) { h->trace = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_max_chunk")) { h->gemm_max_chunk = (int)value; return 0; }
     if (!strcmp(name, "panel_inverse")) { h->panel_inverse = (int)value; return 0; }   // -1 auto, 0 off, 1 on

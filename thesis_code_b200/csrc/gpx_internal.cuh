@@ -84,6 +84,7 @@ struct gpx_handle {
     ncclComm_t comm = nullptr;     // default configuration: bandwidth-bound transfers (predict re-broadcast, all-reduce)
     ncclComm_t comm_lo = nullptr;  // at most 4 CTAs: the panel broadcasts that overlap the trailing updates
     int nccl_lo_ctas = 4;
+    int nccl_full_from_pct = 72;   // panel broadcasts use the full-width communicator from this percentage of the panels on
 
     // options
     int outer_tiles = 0;          // 0 = auto: 4 when sharded, else min(16, max(4, nt / 24)) (K of the trailing update)

@@ -13,9 +13,10 @@ cap() {  # name regex skip
 }
 cap kbuild kbuild_lower_kernel 0
 cap kcross kcross_kernel 0
-cap varreduce var_reduce_kernel 0
+cap varpartial var_partial_kernel 0
 cap bwd bwd_step_kernel 30
 cap fwd fwd_step_kernel 30
-cap gemm "gemm_dmma_kernelILb0" 12
+cap gemm gemm_dmma_kernel 12      # launch 12 = first far update (lookahead off, outer panel 6 tiles at N = 20000)
+cap rowwise gemm_dmma_kernel 660  # a launch inside the variance solve
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/${TAG}_launches.csv python tools/ncu_fit.py $N 2500 > $OUT/${TAG}_launchlist.log 2>&1
 echo "launch list rc=$?"
