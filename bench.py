@@ -254,9 +254,11 @@ def main():
     dvar = torch.empty((Ns,), dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
 
-    def device_step(n=N, ns=Ns):
-        h.fit_device(dX.data_ptr(), n, d, dY.data_ptr(), 1, kid, variance, ls, noise, ARD=ard)
-        h.predict_device(dXs.data_ptr(), ns, dmean.data_ptr(), dvar.data_ptr(), True)
+    from thesis_code_b200 import torch_bridge
+
+    def device_step(n=N, ns=Ns):   # device tensors in / out through the thin torch bridge (thesis_code_b200/torch_bridge.py)
+        torch_bridge.fit(h, dX[:n], dY[:n], kid, variance, ls, noise, ARD=ard)
+        torch_bridge.predict(h, dXs[:ns], out=(dmean[:ns], dvar[:ns]))
 
     def barrier():
         if dist is not None:

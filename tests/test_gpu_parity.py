@@ -653,6 +653,18 @@ def test_caller_stream_ordering_and_device_pointers(gpu_handle):
     gpu_handle.predict_device(dXs.data_ptr(), 300, dmean.data_ptr(), dvar.data_ptr(), True)
     gpu_handle.set_stream(None)
     assert np.array_equal(dmean.cpu().numpy(), ref_mean) and np.array_equal(dvar.cpu().numpy(), ref_var)
+    # the same through the thin torch bridge (tensors in / tensors out on the caller's current stream)
+    from thesis_code_b200 import torch_bridge
+    with torch.cuda.stream(s):
+        dX2 = hX.cuda(non_blocking=True) * 1.0
+        torch_bridge.fit(gpu_handle, dX2, dY, 0, 1.0, ls, 1e-2, ARD=True)
+        tmean, tvar = torch_bridge.predict(gpu_handle, dXs)
+    gpu_handle.set_stream(None)
+    assert np.array_equal(tmean.cpu().numpy(), ref_mean) and np.array_equal(tvar.cpu().numpy(), ref_var)
+    with pytest.raises(ValueError):
+        torch_bridge.fit(gpu_handle, dX2.float(), dY, 0, 1.0, ls, 1e-2, ARD=True)
+    with pytest.raises(TypeError):
+        torch_bridge.predict(gpu_handle, c["Xs"])
 
 
 @pytest.mark.parametrize("cfg,N,Ns,W", [("C3", 3000, 1500, 4), ("C4", 5000, 9000, 16), ("C5", 2100, 700, 5), ("C2", 1300, 300, 13)])

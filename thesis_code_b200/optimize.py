@@ -62,8 +62,9 @@ def optimize_lbfgsb(objective, theta0, positive, x0=None, max_iters=1000, messag
         evals["n"] += 1
         try:
             lml, g = objective(theta)
-        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError):
-            # paramz Model._objective_grads: swallow a few numerical failures and return a huge objective
+        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError, RuntimeError):
+            # paramz Model._objective_grads: swallow a few numerical failures and return a huge objective (RuntimeError covers
+            # the library's own GpxError, e.g. a variance or lengthscale that the Logexp transform underflowed to 0)
             evals["fails"] += 1
             if evals["fails"] > 10:
                 raise
@@ -96,9 +97,16 @@ def hmc_sample(objective, theta0, positive, num_samples, hmc_iters=20, stepsize=
     def to_theta(x):
         return np.where(positive, Logexp.f(x), x)
 
-    def energy_and_grad(x):
+    def energy_and_grad(x, may_fail=True):
         theta = to_theta(x)
-        lml, g = objective(theta)
+        try:
+            lml, g = objective(theta)
+        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError, RuntimeError):
+            if not may_fail:
+                raise
+            # a leapfrog step walked into parameters the model cannot be factorised at: infinite energy, so the
+            # Metropolis test rejects the proposal instead of the whole chain aborting
+            return np.inf, np.zeros(n)
         gx = np.where(positive, Logexp.gradfactor(theta, np.asarray(g, dtype=np.float64)), g)
         return -float(lml), -gx
 
@@ -107,7 +115,7 @@ def hmc_sample(objective, theta0, positive, num_samples, hmc_iters=20, stepsize=
     const = n * np.log(2 * np.pi) / 2.0
     for i in range(num_samples):
         p = np.random.multivariate_normal(np.zeros(n), np.eye(n))
-        U, gU = energy_and_grad(x)
+        U, gU = energy_and_grad(x, may_fail=False)
         H_old = U + const + 0.5 * float(p @ p)
         x_old = x.copy()
         out[i] = to_theta(x)
@@ -117,7 +125,9 @@ def hmc_sample(objective, theta0, positive, num_samples, hmc_iters=20, stepsize=
             U, gU = energy_and_grad(x)
             p = p - 0.5 * stepsize * gU
         H_new = U + const + 0.5 * float(p @ p)
-        accept = 1.0 if H_old > H_new else np.exp(H_old - H_new)
+        if not np.isfinite(H_new):
+            H_new = np.inf
+        accept = 1.0 if H_old > H_new else float(np.exp(H_old - H_new))
         if np.random.rand() < accept:
             out[i] = to_theta(x)
         else:
