@@ -7,15 +7,16 @@
 #include <vector>
 #include "../../thesis_code_b200/csrc/tile_walk.cuh"
 
-static int check(const GemmJob& job, int chunk, const char* what) {
+static int check(const GemmJob& job, int chunk, const char* what, int interleave = 0) {
     const long long slots = 2 * count_slots(job);
-    const long long grid = (slots + chunk - 1) / chunk;
+    const long long grid = gpx_grid_for(slots, chunk, interleave);
     std::map<std::pair<int, int>, int> seen;   // (I, J) -> bitmask of halves
     long long visits = 0;
     for (long long b = 0; b < grid; b++) {
         TileWalk walk;
         walk.init(job);
-        for (long long t = b * chunk; t < (b + 1) * chunk; t++) {
+        const long long t0 = gpx_cta_first_slot(b, chunk, interleave), st = gpx_cta_slot_stride(interleave);
+        for (long long t = t0; t < t0 + (long long)chunk * st; t += st) {
             int I, J, half; bool valid;
             if (!walk.locate(job, t, I, J, half, valid)) break;
             if (!valid) continue;
@@ -86,6 +87,7 @@ int main() {
                 GemmJob j{};
                 j.tri = 1; j.i0 = c0; j.i1 = nt; j.ncols = nt - c0; j.jbase = c0; j.jW = GPX_JW_CONTIG; j.jstride = 0; j.k0 = 0; j.k1 = 1;
                 bad += check(j, chunk, "tri-contig"); cases++;
+                for (int R : {3, 8, 296}) { bad += check(j, chunk, "tri-interleaved", R); cases++; }
                 // rows start below the first column (TRSM-like / inner update shapes)
                 GemmJob r{};
                 r.tri = 0; r.i0 = c0; r.i1 = nt; r.ncols = 1; r.jbase = c0; r.jW = GPX_JW_CONTIG; r.k0 = 0; r.k1 = 1;
@@ -98,6 +100,8 @@ int main() {
                     GemmJob j{};
                     j.tri = 0; j.i0 = 0; j.i1 = nb; j.ncols = nt - p1; j.jbase = p1; j.jW = GPX_JW_CONTIG; j.k0 = 0; j.k1 = 4;
                     bad += check(j, chunk, "rect"); cases++;
+                    bad += check(j, chunk, "rect-interleaved", 296); cases++;
+                    bad += check(j, chunk, "rect-interleaved", 5); cases++;
                 }
             // block-column-cyclic owned columns: panels of W columns, every G-th panel, starting at panel q
             for (int W : {1, 3, 4})
@@ -108,6 +112,7 @@ int main() {
                         GemmJob j{};
                         j.tri = 1; j.i0 = q * W; j.i1 = nt; j.ncols = ncols; j.jbase = q * W; j.jW = W; j.jstride = W * G; j.k0 = 0; j.k1 = W;
                         bad += check(j, chunk, "tri-cyclic"); cases++;
+                        bad += check(j, chunk, "tri-cyclic-interleaved", 296); cases++;
                     }
         }
     }

@@ -113,12 +113,19 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob jo
     int stage = 0;
     uint32_t phase = 0;
     const int nslice = GPX_TILE / kStageK;  // 8 slices per operand tile
-    const long long t_begin = (long long)blockIdx.x * job.chunk, t_end = t_begin + job.chunk;
+    // Slots of this CTA.  Contiguous mode (job.interleave == 0): [b * chunk, (b + 1) * chunk).  Interleaved mode: the R CTAs of
+    // a "round" (R = the number of CTAs resident on the GPU, dispatched in blockIdx order) share a window of R * chunk
+    // consecutive slots and each walks it with stride R, so at any moment the resident CTAs work on ~R NEIGHBOURING slots:
+    // the operand panels they touch (a few tile rows of A, one strip of B) stay in L2, whereas with contiguous chunks the
+    // resident set spans R * chunk slots -- at chunk 16 that is the whole A panel, re-fetched from HBM strip after strip.
+    const long long R = gpx_cta_slot_stride(job.interleave);
+    const long long t_begin = gpx_cta_first_slot(blockIdx.x, job.chunk, job.interleave);
+    const long long t_end = t_begin + (long long)job.chunk * R;
 
     if (warp == kConsumerWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
-            for (long long t = t_begin; t < t_end; t++) {
+            for (long long t = t_begin; t < t_end; t += R) {
                 int I, J, half; bool valid;
                 if (!walk.locate(job, t, I, J, half, valid)) break;
                 if (!valid) continue;
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_dmma_kernel(const GemmJob jo
         // accumulator fragment (i,j) of row half h lives at tile offset  (wn*4 + j) * 1024 + (h*64 + wm*rows + i*8 + g) * 8 + 2*tq
         const int c_off0 = (wn * 4) * 1024 + (wm * kWarpRows + g) * 8 + 2 * tq;
 
-        for (long long t = t_begin; t < t_end; t++) {
+        for (long long t = t_begin; t < t_end; t += R) {
             int I, J, half; bool valid;
             if (!walk.locate(job, t, I, J, half, valid)) break;
             if (!valid) continue;
@@ -259,6 +266,10 @@ long long gpx_launch_gemm(const GemmJob& job_in, int num_sms, cudaStream_t st, i
     }
     job.chunk = (int)chunk;
     int grid = (int)((slots + chunk - 1) / chunk);
+    // interleaved slot assignment (see the kernel) whenever a CTA owns more than one slot; the row-wise panel solve needs
+    // its contiguous half tile row
+    job.interleave = (job.rowwise || chunk == 1 || job.interleave < 0) ? 0 : resident;
+    grid = (int)gpx_grid_for(slots, (int)chunk, job.interleave);
     if (job.overwrite)
         gemm_dmma_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(job);
     else

@@ -52,6 +52,7 @@ void gemm(gpx_t* h, const GemmJob& job_in, cudaStream_t st) {
     GemmJob job = job_in;
     job.chunk = h->gemm_max_chunk > 0 ? h->gemm_max_chunk : (h->world > 1 ? 4 : 16);
     job.strip = h->gemm_strip;
+    job.interleave = h->gemm_interleave ? 0 : -1;
     // Only launches on the main (update) stream are timed and counted: the panel-factorisation GEMMs of stream F
     // overlap them, so adding their durations would count the same wall time twice.
     if (!h->gemm_timing || st != h->st) {
@@ -438,6 +439,7 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "nccl_full_from_pct")) { h->nccl_full_from_pct = (int)value; return 0; }  // 100 = low-CTA communicator throughout
     if (!strcmp(name, "trace")) { h->trace = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_max_chunk")) { h->gemm_max_chunk = (int)value; return 0; }
+    if (!strcmp(name, "gemm_interleave")) { h->gemm_interleave = value ? 1 : 0; return 0; }
     if (!strcmp(name, "panel_inverse")) { h->panel_inverse = (int)value; return 0; }   // -1 auto, 0 off, 1 on
     if (!strcmp(name, "gemm_strip")) { if (value < 0 || value > 64) return fail(h, -1, "gemm_strip out of range"); h->gemm_strip = (int)value; return 0; }
     if (!strcmp(name, "reserve_rows")) { if (value < 0) return fail(h, -1, "bad reserve_rows"); h->reserve_rows = value; return 0; }
@@ -1159,7 +1161,7 @@ double gpx_debug_gemm(gpx_t* h, int rows, int cols, int ktiles, int overwrite, i
     g.B = TileMat{ptr<double>(B), ptr<int64_t>(offB), 0};
     g.C = TileMat{ptr<double>(C), ptr<int64_t>(offC), 0};
     g.tri = 0; g.i0 = 0; g.i1 = rows; g.ncols = cols; g.jbase = 0; g.jW = GPX_JW_CONTIG; g.jstride = 0;
-    g.k0 = 0; g.k1 = ktiles; g.bdiag = 0; g.overwrite = overwrite; g.chunk = max_chunk; g.strip = h->gemm_strip;
+    g.k0 = 0; g.k1 = ktiles; g.bdiag = 0; g.overwrite = overwrite; g.chunk = max_chunk; g.strip = h->gemm_strip; g.interleave = h->gemm_interleave ? 0 : -1;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     gpx_launch_gemm(g, h->num_sms, h->st, nullptr);

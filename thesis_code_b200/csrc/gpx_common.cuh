@@ -93,6 +93,8 @@ struct GemmJob {
     int overwrite;     // 1: C = +A*B^T ; 0: C -= A*B^T
     int chunk;         // in: cap on output-tile slots per CTA (0 = default 16); the launcher overwrites it with its choice
     int strip;         // output tile columns per rasterisation strip (0 = default, see tile_walk.cuh)
+    int interleave;    // set by the launcher: 0 = a CTA owns `chunk` consecutive slots; R > 0 = the R resident CTAs of a round
+                       // interleave over a window of R * chunk slots (L2 locality); in: < 0 forces the contiguous mode
     int rowwise;       // 1: "panel solve" mode -- one strip of all ncols columns, each CTA owns ONE half tile row (64 rows) and
                        // walks its columns in DESCENDING order with the contraction cut at the diagonal, k in [k0, min(k1, J+1)):
                        //   C(I, J) = sum_{k <= J} A(I, k) B(J, k)^T  written IN PLACE over A (column J is only read by columns >= J,

@@ -95,6 +95,7 @@ struct gpx_handle {
     int gemm_max_chunk = 0;               // 0 = auto: 16 on one GPU, 4 when sharded (shorter CTAs let the panel
                                           // factorisation and NCCL kernels of the other streams in sooner)
     int gemm_strip = 0;                   // option "gemm_strip": rasterisation strip width of the tile GEMM (0 = default)
+    int gemm_interleave = 1;              // option "gemm_interleave": interleaved slot assignment of the tile GEMM (L2 locality)
     int panel_inverse = -1;               // option "panel_inverse": in-panel variance solve through inverted diagonal blocks
                                           // (-1 auto: predicts with >= 64 test tiles on one GPU; 0 off; 1 on)
     int minv_active = 0;                  // set by gpx_predict around its batch loop

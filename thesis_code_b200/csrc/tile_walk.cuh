@@ -98,3 +98,18 @@ inline long long count_slots(const GemmJob& j) {
     return total;
 }
 
+
+// ---- slot -> CTA assignment ---------------------------------------------------------------------------------------
+// Contiguous (interleave == 0): CTA b owns [b * chunk, (b + 1) * chunk).  Interleaved (interleave == R): the R CTAs of round
+// g = b / R share the window [g R chunk, (g + 1) R chunk) and CTA b walks it from g R chunk + b % R with stride R.
+__host__ __device__ __forceinline__ long long gpx_cta_first_slot(long long b, int chunk, int interleave) {
+    return interleave > 0 ? (b / interleave) * (long long)interleave * chunk + (b % interleave) : b * chunk;
+}
+__host__ __device__ __forceinline__ long long gpx_cta_slot_stride(int interleave) { return interleave > 0 ? interleave : 1; }
+// number of CTAs that covers `slots` half-tile slots
+inline long long gpx_grid_for(long long slots, int chunk, int interleave) {
+    if (interleave <= 0) return (slots + chunk - 1) / chunk;
+    const long long window = (long long)interleave * chunk;
+    const long long full = slots / window, rest = slots - full * window;
+    return full * interleave + (rest > interleave ? interleave : rest);
+}
