@@ -551,6 +551,16 @@ def test_small_batch_predict_latency_path(gpu_handle, graph):
     gpu_handle.set_option("predict_graph", 1)
 
 
+def test_empty_test_set_returns_empty_arrays():
+    c = synthetic.make_config("C2", N=300, Ns=5)
+    m = GPModel.from_config(c["model"]["kwargs"]); m.init(c["X"], c["Y"])
+    mean, var = m.get_statistics(np.zeros((0, 10)), full_cov=False)
+    assert mean.shape == (1, 0, 1) and var.shape == (1, 0, 1)
+    mean, cov = m.get_statistics(np.zeros((0, 10)), full_cov=True)
+    assert mean.shape == (1, 0, 1) and cov.shape == (1, 0, 0, 1)
+    assert m.get_mean(np.zeros((0, 10))).shape == (1, 0, 1)
+
+
 def test_get_mean_is_the_fast_path_and_counts_few_launches():
     c = synthetic.make_config("C1")
     m = GPModel.from_config(c["model"]["kwargs"]); m.init(c["X"], c["Y"])

@@ -446,6 +446,8 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         covar = np.zeros((T, num_X, num_X, num_obj)) if full_cov else None
         var = None if (full_cov or not want_var) else np.zeros((T, num_X, num_obj))
         fused_y = bool(self._normalize_output)
+        if num_X == 0:                      # nothing to predict: empty arrays of the right shape, no device work
+            return (mean, covar) if full_cov else (mean, var)
         for i, theta in enumerate(self._current_thetas):
             h = self._handle_for_theta(theta)
             if full_cov:

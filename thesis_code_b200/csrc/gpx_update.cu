@@ -88,6 +88,128 @@ __global__ void row_gemv_apply_kernel(const double* __restrict__ partial, int ro
     b[(int64_t)o * Np + (int64_t)(i0 + i) * GPX_TILE + r] -= s;
 }
 
+// ---- GEMV-style append of k <= 8 observations that fit into the partially filled last tile -----------------------------
+// After the forward substitutions z_a = L^-1 k(X, x_new_a) (fwd_step, k right-hand sides) one CTA finishes the job:
+//   S = K(new, new) + (noise + jitter) I - Z Z^T,  C = chol(S)                  (the k x k Schur complement)
+//   new rows of L:      L[N0 + a][j] = z_a[j] (j < N0),  L[N0 + a][N0 + b] = C[a][b]
+//   new rows of Linv_t: [-C^-1 (B A^-1), C^-1]  with B = the new rows' entries inside the last tile, A^-1 = its old inverse block
+//   new entries of z_y: C^-1 (resid_new - Z z_y)                                 (z_y = L^-1 (Y - m), kept from the fit)
+// The kernel entries follow the K-build's arithmetic (Gram trick, exact zero on the diagonal, sqrt, / lengthscale).
+constexpr int kAppMax = 8;
+struct AppendArgs {
+    const double* z;        // [k][Np]
+    const double* xt;       // [k][d] loaded new inputs
+    const double* xtsq;     // [k]
+    double* zy;             // [O][Np]  (zkeep)
+    const double* resid;    // [O][Np]
+    double* linv_tile;      // inverted diagonal tile of the last tile column
+    int* info;
+    int64_t N0, Np;
+    int k, d, O, t0, r0, kernel_id;
+    double variance, rdiv, diag_add;
+};
+
+__device__ __forceinline__ double block_sum_1024(double v, double* red) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < 32; w++) s += red[w];   // every thread sums the 32 warp partials in the same order
+    return s;
+}
+
+__global__ void __launch_bounds__(1024) append_finish_kernel(TileMat L, AppendArgs a) {
+    __shared__ double red[32];
+    __shared__ double S[kAppMax][kAppMax], C[kAppMax][kAppMax], Ci[kAppMax][kAppMax], D[kAppMax][kAppMax], T[kAppMax][GPX_TILE];
+    __shared__ int bad;
+    const int tid = threadIdx.x, k = a.k;
+    if (tid == 0) bad = 0;
+    // Schur complement and Z z_y
+    for (int p = 0; p < k; p++)
+        for (int q = 0; q <= p; q++) {
+            double s = 0.0;
+            for (int64_t j = tid; j < a.N0; j += 1024) s = fma(a.z[(int64_t)p * a.Np + j], a.z[(int64_t)q * a.Np + j], s);
+            s = block_sum_1024(s, red);
+            if (tid == 0) {
+                double dot = 0.0;
+                for (int c = 0; c < a.d; c++) dot = fma(a.xt[p * a.d + c], a.xt[q * a.d + c], dot);
+                double r2 = fmax(-2.0 * dot + (a.xtsq[p] + a.xtsq[q]), 0.0);
+                if (p == q) r2 = 0.0;
+                double kv = gpx_k_of_r(a.kernel_id, a.variance, gpx_scaled_r(r2, a.rdiv));
+                if (p == q) kv += a.diag_add;
+                S[p][q] = kv - s;
+            }
+        }
+    for (int p = 0; p < k; p++)
+        for (int o = 0; o < a.O; o++) {
+            double s = 0.0;
+            for (int64_t j = tid; j < a.N0; j += 1024) s = fma(a.z[(int64_t)p * a.Np + j], a.zy[(int64_t)o * a.Np + j], s);
+            s = block_sum_1024(s, red);
+            if (tid == 0) D[p][o] = s;
+        }
+    __syncthreads();
+    if (tid == 0) {
+        for (int p = 0; p < k; p++)
+            for (int q = 0; q <= p; q++) {
+                double s = S[p][q];
+                for (int m = 0; m < q; m++) s -= C[p][m] * C[q][m];
+                if (p == q) {
+                    if (!(s > 0.0)) { atomicCAS(a.info, 0, (int)(a.N0 + p + 1)); bad = 1; s = 1.0; }
+                    C[p][p] = sqrt(s);
+                } else {
+                    C[p][q] = s / C[q][q];
+                }
+            }
+        for (int p = 0; p < k; p++)       // inverse of the lower-triangular C
+            for (int q = 0; q <= p; q++) {
+                double s = (p == q) ? 1.0 : 0.0;
+                for (int m = q; m < p; m++) s -= C[p][m] * Ci[m][q];
+                Ci[p][q] = s / C[p][p];
+            }
+        for (int p = 0; p < k; p++)       // z_y of the new rows
+            for (int o = 0; o < a.O; o++) {
+                double s = 0.0;
+                for (int q = 0; q <= p; q++) s += Ci[p][q] * (a.resid[(int64_t)o * a.Np + a.N0 + q] - D[q][o]);
+                a.zy[(int64_t)o * a.Np + a.N0 + p] = s;
+            }
+    }
+    __syncthreads();
+    if (bad) return;
+    // new rows of L
+    for (int p = 0; p < k; p++) {
+        const int row = a.r0 + p;
+        for (int64_t j = tid; j < a.N0; j += 1024)
+            tile_ptr(L, a.t0, (int)(j >> 7))[gpx_tile_idx(row, (int)(j & 127))] = a.z[(int64_t)p * a.Np + j];
+        if (tid < GPX_TILE - a.r0) {     // the tile columns of the new block and of the identity padding behind it
+            const int q = tid;
+            const double v = q < k ? (q <= p ? C[p][q] : 0.0) : 0.0;
+            tile_ptr(L, a.t0, a.t0)[gpx_tile_idx(row, a.r0 + q)] = v;
+        }
+    }
+    // new rows of the inverted diagonal tile: T = B A^-1 (A^-1 lower triangular), rows = [-C^-1 T, C^-1]
+    if (tid < a.r0) {
+        const int c = tid;
+        for (int p = 0; p < k; p++) {
+            double s = 0.0;
+            for (int cc = c; cc < a.r0; cc++)
+                s = fma(a.z[(int64_t)p * a.Np + (int64_t)a.t0 * GPX_TILE + cc], a.linv_tile[gpx_tile_idx(cc, c)], s);
+            T[p][c] = s;
+        }
+    }
+    __syncthreads();
+    if (tid < GPX_TILE) {
+        const int c = tid;
+        for (int p = 0; p < k; p++) {
+            double v = 0.0;
+            if (c < a.r0) { for (int q = 0; q <= p; q++) v -= Ci[p][q] * T[q][c]; }
+            else if (c - a.r0 < k) { const int q = c - a.r0; v = q <= p ? Ci[p][q] : 0.0; }
+            a.linv_tile[gpx_tile_idx(a.r0 + p, c)] = v;
+        }
+    }
+    gpx_publish_for_async_proxy();
+}
+
 // v[i] = fixed pseudo-random value in (-1, 1) for i < N, 0 for the padding (splitmix64 of the index)
 __global__ void fill_random_kernel(double* __restrict__ v, int64_t N, int64_t Np) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -358,6 +480,73 @@ int kmatvec(gpx_t* h, const double* vec, double* out, DevBuf& partial, int t0, i
 
 }  // namespace
 
+// gpx_append for k <= 8 observations that fit into the partially filled last tile: k forward substitutions (one pass over
+// L for all of them), one finishing CTA, the backward substitution -- no 128-row tile work.  Returns 1000 if it does not apply.
+static int append_vec(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem) {
+    const int d = h->d, O = h->O, nt = h->nt, W = h->W;
+    const int64_t N0 = h->N, Np = h->Np;
+    const int r0 = (int)(N0 % GPX_TILE), t0 = (int)(N0 / GPX_TILE);
+    if (k > kAppMax || r0 == 0 || r0 + k > GPX_TILE || O > kAppMax || !h->zkeep_valid || t0 != nt - 1) return 1000;
+    int rc = small_workspace(h);
+    if (rc) return rc;
+    const SmallWs w = small_views(h);
+    cudaStream_t st = h->st;
+    double* pin = reinterpret_cast<double*>(h->pin);
+    double* dY = w.var;   // k * O <= 128 * O doubles of scratch
+    if (mem == GPX_MEM_HOST) {
+        memcpy(pin, Xn, (size_t)k * d * 8);
+        memcpy(pin + GPX_TILE * d, Yn, (size_t)k * O * 8);
+        GPX_CUDA(h, cudaMemcpyAsync(w.Xin, pin, (size_t)k * d * 8, cudaMemcpyHostToDevice, st));
+        GPX_CUDA(h, cudaMemcpyAsync(dY, pin + GPX_TILE * d, (size_t)k * O * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        GPX_CUDA(h, cudaMemcpyAsync(w.Xin, Xn, (size_t)k * d * 8, cudaMemcpyDeviceToDevice, st));
+        GPX_CUDA(h, cudaMemcpyAsync(dY, Yn, (size_t)k * O * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    h->fitted = false;
+    GPX_CUDA(h, cudaMemsetAsync(h->info.p, 0, 64, st));
+    prep_inputs(h, w.Xin, k, k, ptr<double>(h->Xs) + N0 * d, ptr<double>(h->xsq) + N0, st);          // into the training set
+    prep_inputs(h, w.Xin, k, GPX_TILE, w.Xt, w.xtsq, st);                                             // aligned copy for the tile builder
+    resid_append_kernel<<<(int)((k * O + 255) / 256), 256, 0, st>>>(dY, k, O, h->mean_const, ptr<double>(h->resid), Np, N0, k);
+    gpx_launch_kcross(TileMat{nullptr, nullptr, 0}, 1, 1, nt, w.Xt, w.xtsq, k, ptr<double>(h->Xs), ptr<double>(h->xsq), N0, d,
+                      h->kernel_id, h->variance, h->rdiv, nullptr, 0, Np, nullptr, st, w.b, (int)k);
+    for (int J = 0; J < nt; J++)
+        gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, w.b, w.z, Np, (int)k, 2 * h->num_sms, st);
+    AppendArgs a{};
+    a.z = w.z; a.xt = w.Xt; a.xtsq = w.xtsq; a.zy = ptr<double>(h->zkeep); a.resid = ptr<double>(h->resid);
+    a.linv_tile = ptr<double>(h->linv) + (int64_t)t0 * GPX_TILE_ELEMS; a.info = ptr<int>(h->info);
+    a.N0 = N0; a.Np = Np; a.k = (int)k; a.d = d; a.O = O; a.t0 = t0; a.r0 = r0; a.kernel_id = h->kernel_id;
+    a.variance = h->variance; a.rdiv = h->rdiv; a.diag_add = h->noise + h->jitter;
+    append_finish_kernel<<<1, 1024, 0, st>>>(lmat(h), a);
+    h->launches += 3 + nt;
+    h->N = N0 + k;
+    h->gen++;
+    if (h->minv_valid > t0 / W) h->minv_valid = t0 / W;
+    // alpha: backward substitution over the whole factor (it consumes its right-hand side: a copy of the kept z), then the LML
+    GPX_CUDA(h, cudaMemcpyAsync(h->work2.p, h->zkeep.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
+    rc = backward_solve(h);
+    gpx_launch_lml(ptr<double>(h->linv), ptr<double>(h->alpha), ptr<double>(h->resid), (int64_t)nt * GPX_TILE, Np, O, ptr<double>(h->scal), st);
+    h->launches++;
+    double hs[2] = {0, 0};
+    int hinfo = 0;
+    cudaMemcpyAsync(hs, h->scal.p, 16, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&hinfo, h->info.p, 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc) return rc;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, -2, "CUDA error during append: %s", cudaGetErrorString(e));
+    if (hinfo != 0) {
+        h->zkeep_valid = false;
+        fail(h, hinfo, "append: Ky is not positive definite: non-positive pivot at row %d", hinfo);
+        return hinfo;
+    }
+    h->logdet = hs[0];
+    h->quad = hs[1];
+    const double log2pi = 1.8378770664093454835606594728112;
+    h->lml = 0.5 * (-(double)h->N * O * log2pi - (double)O * h->logdet - h->quad);
+    h->fitted = true;
+    return 0;
+}
+
 // ====================================================================================================================
 int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int var_cols, int include_noise,
                       int mem) {
@@ -474,6 +663,10 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     if (h->fit_norm_x || h->fit_norm_y) return fail(h, -8, "gpx_append: the normaliser statistics change with the data (refit)");
     GPX_CUDA(h, cudaSetDevice(h->device));
     { int rcw = wait_for_caller(h); if (rcw) return rcw; }
+    {   // a handful of points inside the current tile: the GEMV-style path
+        const int rv = append_vec(h, Xn, k, Yn, mem);
+        if (rv != 1000) return rv;
+    }
     const int d = h->d, O = h->O, W = h->W;
     const int64_t N0 = h->N, N1 = N0 + k;
     const int t0 = (int)(N0 / GPX_TILE), nt1 = (int)((N1 + GPX_TILE - 1) / GPX_TILE);
