@@ -137,6 +137,29 @@ def test_normalizer_model_contract_without_gpu(tmp_path):
     assert n.denormalize_covariance(np.ones((1, 5, 5, 1))).shape == (1, 5, 5, 1, 2)   # the reference's trailing-axis quirk
 
 
+def test_priors_restate_gpy_formulas():
+    """thesis_code_b200.priors (GPy 1.9.6 priors.py restated) against scipy.stats, gradients against finite differences,
+    and the Logexp log-Jacobian paramz adds for a prior on a transformed parameter."""
+    import scipy.stats as st
+    from thesis_code_b200 import optimize, priors
+    x = np.array([0.3, 1.7, 4.0])
+    np.testing.assert_allclose(priors.Gamma(2.5, 3.0).lnpdf(x), st.gamma.logpdf(x, 2.5, scale=1 / 3.0), rtol=1e-13)
+    np.testing.assert_allclose(priors.LogGaussian(0.2, 0.7).lnpdf(x), st.lognorm.logpdf(x, 0.7, scale=np.exp(0.2)), rtol=1e-13)
+    np.testing.assert_allclose(priors.Gaussian(1.0, 2.0).lnpdf(x), st.norm.logpdf(x, 1.0, 2.0), rtol=1e-13)
+    g = priors.Gamma.from_EV(2.0, 0.5)
+    assert abs(g.a / g.b - 2.0) < 1e-14 and abs(g.a / g.b ** 2 - 0.5) < 1e-14
+    for p in (priors.Gamma(2.5, 3.0), priors.LogGaussian(0.2, 0.7), priors.Gaussian(1.0, 2.0)):
+        fd = (p.lnpdf(x + 1e-6) - p.lnpdf(x - 1e-6)) / 2e-6
+        np.testing.assert_allclose(p.lnpdf_grad(x), fd, rtol=1e-6)
+        assert priors.is_prior(p) and np.all(np.isfinite(p.rvs(5)))
+    assert not priors.is_prior(object()) and not priors.is_prior(0.1)
+    f = np.array([0.5, 2.0, 40.0])
+    fd = (optimize.Logexp.log_jacobian(f + 1e-6) - optimize.Logexp.log_jacobian(f - 1e-6)) / 2e-6
+    np.testing.assert_allclose(optimize.Logexp.log_jacobian_grad(f)[:2], fd[:2], rtol=1e-6)
+    m = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True, "noise_prior": priors.Gamma(2.0, 4.0)})
+    assert m._noise_prior_object() is m.noise_prior            # accepted like Gaussian_noise.variance.set_prior(...)
+
+
 def test_sharding_is_opt_in(monkeypatch):
     m = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "noise_prior": 0.1})
     monkeypatch.setenv("WORLD_SIZE", "4")

@@ -346,6 +346,37 @@ def test_do_optimize_follows_gpy_recipe():
     assert np.isfinite(m2.mean_const) and np.sqrt(np.mean((mean2[0] - (Y[:50] + 3.0)) ** 2)) < 0.15
 
 
+def test_do_optimize_with_a_prior_on_the_noise():
+    """noise_prior = prior object (reference core_models.py:206-207: Gaussian_noise.variance.set_prior): MAP instead of ML.
+    The GPU objective + prior must land where the oracle's objective + the same prior lands from the same start, and a
+    strong prior must pull the noise towards its mode."""
+    from thesis_code_b200 import optimize as gopt, priors
+    rng = np.random.RandomState(5)
+    N = 400
+    X = rng.rand(N, 1)
+    Y = np.sin(6 * X) + 0.3 * rng.randn(N, 1)
+    prior = priors.Gamma.from_EV(0.5, 0.0005)                  # tight around 0.5; the data say ~0.09
+    m = GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True, "noise_prior": prior})
+    np.random.seed(11)
+    m.init(X, Y)
+    th = m._current_thetas[0]                                   # [variance, lengthscale, noise]
+
+    def obj(theta):
+        st = o.fit(X, Y, "GPyRBF", theta[0], theta[1:2], False, theta[2])
+        g = o.lml_grad(st)
+        val = st["lml"] + float(prior.lnpdf(theta[2])) + float(gopt.Logexp.log_jacobian(theta[2]))
+        return val, np.array([g[0], g[1], g[2] + float(prior.lnpdf_grad(theta[2])) + float(gopt.Logexp.log_jacobian_grad(theta[2]))])
+    np.random.seed(11)
+    x0 = gopt.randomize(3)
+    x0[-1] = float(gopt.Logexp.finv(prior.rvs(1)[0]))
+    th_o, val_o, _ = gopt.optimize_lbfgsb(obj, [1.0, 1.0, 1.0], [True] * 3, x0=x0)
+    np.testing.assert_allclose(th, th_o, rtol=2e-3)
+    m_ml = GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True})
+    np.random.seed(11)
+    m_ml.init(X, Y)
+    assert 0.05 < m_ml.noise_variance < 0.15 and m.noise_variance > 3 * m_ml.noise_variance     # the prior wins over 400 points
+
+
 def _vanilla_cfg(c):
     """GPVanillaModel(l_v, s) as a GPModel config: RBF(variance 1, lengthscale l_v / sqrt 2), noise s (jitter set to 0)."""
     return {"kernel": {"name": "GPyRBF", "kwargs": {"variance": 1.0, "lengthscale": float(c["lengthscale_v"]) / np.sqrt(2.0)}},

@@ -6,6 +6,7 @@ from .core_models import (BaseModel, DerivativeGPModel, GPModel, MarginalLogLike
                           SaveMixin)
 
 from .normalizer import Normalizer, NormalizerModel  # noqa: F401,E402
+from . import priors  # noqa: F401,E402
 
 __all__ = ["Normalizer", "NormalizerModel", "GPModel", "DerivativeGPModel", "BaseModel", "ProbModel", "SaveMixin", "MarginalLogLikelihoodMixin",
            "GPyRBF", "GPyMatern52", "GPyMatern32", "GPyExponential", "ConfigMixin", "LazyConstructor",

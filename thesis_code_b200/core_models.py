@@ -20,7 +20,7 @@ gradient evaluated on the GPU (``optimize.py``, ``gpx_lml_grad``); ``num_mcmc > 
 objective and predictions gain the leading hyper-sample axis (one resident factorisation per retained sample).
 ``add_observations`` appends to the resident factor (``gpx_append``) when only the data changed; ``get_mean`` and small
 batches take the latency path of ``gpx_predict``; ``predict_jacobian`` / ``predict_hessian`` evaluate the reference's
-expressions from sums computed on the GPU.  Not built: GPy prior objects on the noise (``NotImplementedError``).
+expressions from sums computed on the GPU.  A non-numeric ``noise_prior`` is a prior object with GPy's interface (``priors.py``).
 """
 import os
 import pathlib
@@ -341,8 +341,12 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                     self.noise_variance = float(self.noise_prior)
                     self._noise_fixed = True         # Gaussian_noise.fix(noise_prior)
                 else:
-                    raise NotImplementedError("GPy prior objects on the noise variance are not supported; "
-                                              "pass a number (fixed noise) or None (free noise)")
+                    # Gaussian_noise.variance.set_prior(noise_prior) (reference core_models.py:206-207): any object with GPy's
+                    # prior interface (lnpdf / lnpdf_grad / rvs) -- thesis_code_b200.priors restates GPy's Gamma / LogGaussian / Gaussian
+                    from . import priors as _priors
+                    if not _priors.is_prior(self.noise_prior):
+                        raise NotImplementedError("noise_prior must be a number (fixed noise), None (free noise) or an object "
+                                                  "with GPy's prior interface lnpdf / lnpdf_grad / rvs (see thesis_code_b200.priors)")
         if self.do_optimize and self._wants_sharding() and int(os.environ.get("WORLD_SIZE", "1")) > 1:
             raise _gpx.GpxError("do_optimize / num_mcmc need gpx_lml_grad, which is not available on a sharded handle: "
                                 "optimise on one GPU (model.distributed = False), then refit sharded with do_optimize=False")
@@ -398,17 +402,33 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
             if not self._noise_fixed:
                 self.noise_variance = float(theta[i + 1 + nl])
 
+        prior = self._noise_prior_object()
+
         def objective(theta):
             unpack(theta)
             self._factorize(retry=True)   # GPy's inference runs jitchol inside every objective evaluation
             h = self._get_handle()
             g = h.lml_grad(nl)            # [variance, ls..., noise, mean]
             out = ([g[nl + 2]] if has_mean else []) + [g[0]] + list(g[1:1 + nl]) + ([] if self._noise_fixed else [g[nl + 1]])
-            return h.lml()[0], np.array(out)
+            value, out = h.lml()[0], np.array(out)
+            if prior is not None:
+                # paramz Priorizable: objective = -(log likelihood + log prior), the log prior of a transformed parameter
+                # includes the log Jacobian of the Logexp transform
+                from .optimize import Logexp
+                s2 = self.noise_variance
+                value = value + float(np.sum(prior.lnpdf(np.array([s2])))) + float(Logexp.log_jacobian(s2))
+                out[-1] += float(np.sum(prior.lnpdf_grad(np.array([s2])))) + float(Logexp.log_jacobian_grad(s2))
+            return value, out
 
         theta0 = np.array(([self.mean_const] if has_mean else []) + [float(self.kernel.variance[0])] +
                           list(self.kernel.lengthscale) + ([] if self._noise_fixed else [self.noise_variance]))
         return names, positive, unpack, objective, theta0
+
+    def _noise_prior_object(self):
+        from . import priors as _priors
+        if self.noise_prior and not isinstance(self.noise_prior, (float, int)) and not self._noise_fixed and _priors.is_prior(self.noise_prior):
+            return self.noise_prior
+        return None
 
     def _sample_hyperparameters(self):
         """``GPy.inference.mcmc.HMC(gpy_model, stepsize).sample(...)`` then burn-in / thinning (core_models.py:212-219).
@@ -432,6 +452,9 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
         x0 = None
         if getattr(self, "randomize_before_optimize", True):
             x0 = gopt.randomize(theta0.size)      # GPy randomizes the mean constant too (unconstrained N(0,1) draw)
+            prior = self._noise_prior_object()
+            if prior is not None:                 # ... and draws a priored parameter from its prior (paramz Priorizable.randomize)
+                x0[-1] = float(gopt.Logexp.finv(np.asarray(prior.rvs(1), dtype=np.float64)[0]))
         theta, lml, info = gopt.optimize_lbfgsb(objective, theta0, positive, x0=x0, max_iters=getattr(self, "max_iters", 1000))
         unpack(theta)
         self._factorize()

@@ -33,6 +33,18 @@ class Logexp:
         f = np.asarray(f, dtype=np.float64)
         return df * np.where(f > _LIM_VAL, 1.0, -np.expm1(-f))
 
+    # a prior on a Logexp-transformed parameter is a density on the constrained value; the optimiser works on the
+    # unconstrained one, so paramz adds the log Jacobian of the transform to the log prior (and its derivative)
+    @staticmethod
+    def log_jacobian(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f > _LIM_VAL, f, np.log(np.expm1(f))) - f
+
+    @staticmethod
+    def log_jacobian_grad(f):
+        f = np.asarray(f, dtype=np.float64)
+        return 1.0 / np.expm1(f)
+
 
 def randomize(n, rand_gen=None):
     """paramz ``randomize``: transformed parameters ~ N(0, 1) (global numpy RNG unless ``rand_gen`` is given)."""
