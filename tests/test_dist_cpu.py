@@ -88,6 +88,21 @@ assert bool((mine == 1).all())
 lo, hi = gd.test_tile_shard(2500, rank, world)
 t = torch.tensor([hi - lo]); dist.all_reduce(t)
 assert int(t) == gd.num_tiles(2500)
+# a sharded fit is a collective over identical inputs: the fingerprint check passes on equal data and raises -- on every
+# rank, instead of hanging -- when one rank was given something else (data or hyper-parameters)
+X = np.linspace(0, 1, 40).reshape(20, 2); Y = np.sin(X[:, :1]); theta = np.array([1.0, 0.5, 0.01])
+gd.check_same_problem(h, X, Y, theta, dist)
+for bad in ("X", "theta"):
+    Xr = X + (1e-9 if (bad == "X" and rank == 1) else 0.0)
+    tr = theta * (1.0 + (1e-12 if (bad == "theta" and rank == 1) else 0.0))
+    try:
+        gd.check_same_problem(h, Xr, Y, tr, dist)
+        raise SystemExit("mismatch in %s not detected" % bad)
+    except RuntimeError as e:
+        assert "different data or hyper-parameters" in str(e), e
+# the bench's agreement on the number of timed steps: min over ranks
+t = torch.tensor([float(3 + rank)]); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+assert int(t) == 3
 dist.destroy_process_group()
 print("OK", rank)
 """

@@ -522,7 +522,15 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     }
     for (int p = 0; p < h->npanels; p++) { int64_t e = panel_elems(h, p); if (e > max_panel) max_panel = e; }
     int rc;
-    if ((rc = ensure(h, h->L, (size_t)(off > 0 ? off : 1) * 8))) return rc;
+    if ((rc = ensure(h, h->L, (size_t)(off > 0 ? off : 1) * 8))) {
+        // out of memory: give back everything that is only a cache or a workspace of earlier predicts / appends / larger
+        // fits (they are rebuilt on demand) and try once more
+        for (DevBuf* b : {&h->Tt, &h->mean_partial, &h->sp, &h->minv, &h->ywork, &h->var_partial, &h->dmean, &h->dvar, &h->Xt,
+                          &h->xtsq, &h->zkeep, &h->cache, &h->gbuf[0], &h->gbuf[1], &h->stage})
+            release(h, *b);
+        h->sp_key[0] = -1; h->minv_valid = 0; h->minv_layout_cap = -1; h->zkeep_valid = false;
+        if ((rc = ensure(h, h->L, (size_t)(off > 0 ? off : 1) * 8))) return rc;
+    }
     if ((rc = ensure(h, h->linv, (size_t)cap_nt * GPX_TILE_BYTES))) return rc;
     if ((rc = ensure(h, h->coloff, (size_t)cap_nt * 8))) return rc;
     if ((rc = ensure(h, h->vcoloff, (size_t)nt * 8))) return rc;
@@ -1006,6 +1014,8 @@ int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double
     const int nt = h->nt, d = h->d, O = h->O;
     const int64_t Np = h->Np;
     const int nbt = (int)((Ns + GPX_TILE - 1) / GPX_TILE);
+    if (Ns > 65535) return fail(h, -1, "gpx_predict_cov: at most 65535 test points (the dense covariance would be %.0f GB); use full_cov=False",
+                                (double)Ns * Ns * 8 / 1e9);
     // the whole transposed cross-kernel (nbt x nt tiles) and the packed covariance must be resident at once
     {
         size_t fr = 0, tot = 0;
