@@ -96,12 +96,14 @@ GPX_API int gpx_get_normalizer(gpx_t* h, double* x_mean, double* x_std, double* 
 GPX_API int gpx_set_stream(gpx_t* h, void* stream, int has_stream);
 
 /*
- * APPEND k observations to the fitted model without refactorising (single-GPU handles, no normaliser): the new rows
- * of K are built, solved against the resident factor (the same DMMA triangular solve as the predictive variance), the
- * k x k Schur complement is factored, alpha and the LML are recomputed by two O(N^2) substitutions.  O(k N^2) instead
- * of the O(N^3) refit that BaseModel.add_observations performs (src/models/core_models.py:65-77; called once per
- * Bayesian-optimisation step from src/algorithms.py:120-143).  Returns 0, > 0 (non-positive pivot: the caller refits
- * with jitter), -8 when the handle cannot append (sharded / normalised: the caller refits).
+ * APPEND k observations to the fitted model without refactorising (single-GPU handles, no normaliser).  O(k N^2)
+ * instead of the O(N^3) refit that BaseModel.add_observations performs (src/models/core_models.py:65-77; called once per
+ * Bayesian-optimisation step from src/algorithms.py:120-143).  Up to 8 points that fit into the partially filled last
+ * 128-row tile: k forward substitutions in one pass over L, the k x k Schur complement and the new rows of L / of the
+ * inverted diagonal tile in one finishing CTA, the backward substitution -- no tile work.  Otherwise: the tile rows that
+ * receive observations are rebuilt, solved against the resident factor (the DMMA triangular solve of the predictive
+ * variance, in place), the Schur complement is factored, alpha and the LML are recomputed.  Returns 0, > 0 (non-positive
+ * pivot: the caller refits with jitter), -8 when the handle cannot append (sharded / normalised: the caller refits).
  */
 GPX_API int gpx_append(gpx_t* h, const double* X_new, int64_t k, const double* Y_new, int mem);
 
@@ -177,7 +179,11 @@ GPX_API int64_t gpx_launch_count(const gpx_t* h);
  * "nccl_lo_ctas" (CTA cap of the factorisation communicator, default 4; before gpx_comm_init), "cache_mb" (sharded
  * handles keep received panels resident for later predicts: -1 = as many as fit beside a reserve, 0 = none, else a cap
  * in MB), "trace" (see gpx_trace), "reserve_rows" (row capacity laid out beyond N at fit time so that gpx_append works in
- * place; single GPU), "predict_graph" (1, default: replay the small-batch predict launch chain as a CUDA graph). */
+ * place; single GPU), "predict_graph" (1, default: replay the small-batch predict launch chain as a CUDA graph),
+ * "panel_inverse" (in-panel variance solve through the inverted W x W-tile diagonal blocks: -1 auto = predicts with >= 64 test
+ * tiles on one GPU, 0 off, 1 on), "gemm_strip" (rasterisation strip width of the tile GEMM, 0 = 16), "gemm_interleave" (1,
+ * default: resident CTAs walk neighbouring tile slots), "nccl_full_from_pct" (panel broadcasts switch from the low-CTA to the
+ * full-width communicator at this percentage of the panels, default 72). */
 GPX_API int gpx_set_option(gpx_t* h, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel of this handle is launched on, so that a caller can
  * bracket calls with its own CUDA events (bench.py does, via torch.cuda.ExternalStream). */

@@ -205,3 +205,25 @@ def test_committed_bench_lines_follow_the_contract():
             else:
                 g = c["golden_parity"]
                 assert max(g["mean_normwise"], g["var_normwise"], g["lml_rel"]) < g["gate"] == 1e-8
+
+
+def test_reference_arm_of_bench_runs_on_cpu_and_only_on_rank_0():
+    """`bench.py --impl reference` (the driver's CPU arm): rank 0 prints ONE JSON line with the contract's keys on the CUDA arm's
+    config / metric / unit; the other ranks of a torchrun launch exit 0 without work."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1",
+           "--N", "600", "--Ns", "100"]
+    out0 = subprocess.run(cmd, env=dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0"), capture_output=True, text=True, timeout=300)
+    assert out0.returncode == 0, out0.stderr[-2000:]
+    lines = [l for l in out0.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "TFLOP/s" and d["higher_is_better"] is True and d["n_gpus"] == 2
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["steps_requested"] == 2
+    assert d["config"]["N"] == 200000 and d["config"]["workload"].startswith("C5")        # the CUDA arm's config, not the sample's
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["sample_N"] == 600 and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    out1 = subprocess.run(cmd, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), capture_output=True, text=True, timeout=300)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""

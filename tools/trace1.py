@@ -6,9 +6,11 @@ c = synthetic.make_config("C5", N=N, Ns=256)
 kk = c['model']['kwargs']['kernel']['kwargs']
 h = _gpx.Handle(0); h.set_option("outer_tiles", W); h.set_option("trace", 1)
 for rep in range(2):
-    h.fit(c['X'], c['Y'], 0, 1.0, np.array(kk['lengthscale']), 1e-2)
+    h.fit(c['X'], c['Y'], 0, 1.0, np.array(kk['lengthscale']), 1e-2, ARD=True)
 tr = h.trace(); ph = h.phase_ms()
 nt = (N + 127) // 128
+if W == 0:   # auto panel width: recover it from the number of panels
+    W = next(w for w in range(1, 65) if (nt + w - 1) // w == tr.shape[0])
 print("N", N, "W", W, "chol ms", ph['cholesky'], "TF/s", N**3/3/ph['cholesky']/1e9)
 fact = tr[:, 1] - tr[:, 0]; a = tr[:, 3] - tr[:, 2]; f = tr[:, 4] - tr[:, 3]; b = tr[:, 5] - tr[:, 4]
 gaps = tr[1:, 2] - tr[:-1, 5]
