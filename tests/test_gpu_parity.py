@@ -735,3 +735,29 @@ def test_panel_inverse_variance_solve_matches_stepwise_and_oracle(cfg, N, Ns, W)
     mean, var = m.get_statistics(c["Xs"], full_cov=False)
     omean, ovar = om.get_statistics(c["Xs"], full_cov=False)
     assert normwise(mean, omean) < TOL and normwise(var, ovar) < TOL
+
+
+def test_inverted_panel_blocks_survive_appends():
+    """The inverted diagonal blocks are shared by the variance solve and gpx_append and are updated incrementally: blocks of
+    panels an append does not touch are kept, the others (and a re-laid-out storage) are rebuilt -- predictions through them
+    must keep matching the oracle after tile-route appends, GEMV-route appends and a re-layout."""
+    c = synthetic.make_config("C5", N=3000, Ns=400)
+    kw = c["model"]["kwargs"]
+    X, Y = c["X"], c["Y"]
+    m = GPModel.from_config(kw)
+    h = m._get_handle()
+    h.set_option("outer_tiles", 4)
+    h.set_option("panel_inverse", 1)
+    m.init(X[:2000], Y[:2000])
+    m.get_statistics(c["Xs"], full_cov=False)                 # builds every block
+    n = 2000
+    for k in (3, 200, 1, 1, 500, 7):                          # GEMV route, tile route (new tile rows, re-layout), ...
+        m.add_observations(X[n:n + k], Y[n:n + k]); n += k
+        mean, var = m.get_statistics(c["Xs"], full_cov=False)
+        om = o.OracleGPModel(kernel=kw["kernel"], noise_prior=kw["noise_prior"]); om.init(X[:n], Y[:n])
+        omean, ovar = om.get_statistics(c["Xs"], full_cov=False)
+        assert normwise(mean, omean) < TOL and normwise(var, ovar) < TOL, (n, k)
+        h.set_option("panel_inverse", 0)
+        mean0, var0 = m.get_statistics(c["Xs"], full_cov=False)
+        h.set_option("panel_inverse", 1)
+        assert normwise(var, var0) < 1e-10
