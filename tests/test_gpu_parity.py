@@ -172,8 +172,8 @@ def test_add_observations_refits_and_pickle_roundtrip(tmp_path):
     m.save(str(tmp_path / "model"))
     m2 = GPModel.load(str(tmp_path / "model"))
     assert m2._handle is None
-    mean2, var2 = m2.get_statistics(c["Xs"], full_cov=False)      # re-factorises lazily on the GPU
-    assert np.array_equal(mean2, mean) and np.array_equal(var2, var)
+    mean2, var2 = m2.get_statistics(c["Xs"], full_cov=False)      # re-factorises lazily on the GPU (a full fit of all 600 rows)
+    assert normwise(mean2, mean) < 1e-11 and normwise(var2, var) < 1e-11
 
 
 def test_not_positive_definite_is_reported_and_retried(gpu_handle):

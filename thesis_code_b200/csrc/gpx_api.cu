@@ -50,7 +50,10 @@ NcclApi& nccl() {
 // every DMMA tile-GEMM launch goes through here (optionally bracketed by events for the roofline numbers)
 void gemm(gpx_t* h, const GemmJob& job_in, cudaStream_t st) {
     GemmJob job = job_in;
-    job.chunk = h->gemm_max_chunk > 0 ? h->gemm_max_chunk : (h->world > 1 ? 4 : 16);
+    // Cap on tile slots per CTA.  With the interleaved slot assignment long chunks no longer buy L2 locality, and short CTAs let
+    // the high-priority panel kernels of the look-ahead stream in as soon as they are ready: cap 16 -> 2 on one GPU is +1.8 % on
+    // the C4 Cholesky, +4 % at N = 40000, +12 % at N = 20000 (profiles/r02_gemm_experiments.txt); 1 and 2 are equal within 0.1 %.
+    job.chunk = h->gemm_max_chunk > 0 ? h->gemm_max_chunk : (h->world > 1 ? 4 : 2);
     job.strip = h->gemm_strip;
     job.interleave = h->gemm_interleave ? 0 : -1;
     // Only launches on the main (update) stream are timed and counted: the panel-factorisation GEMMs of stream F

@@ -92,7 +92,7 @@ struct gpx_handle {
     int sync_phases = 1;
     int gemm_timing = 0;
     int lookahead = 1;
-    int gemm_max_chunk = 0;               // 0 = auto: 16 on one GPU, 4 when sharded (shorter CTAs let the panel
+    int gemm_max_chunk = 0;               // 0 = auto: 2 on one GPU, 4 when sharded (shorter CTAs let the panel
                                           // factorisation and NCCL kernels of the other streams in sooner)
     int gemm_strip = 0;                   // option "gemm_strip": rasterisation strip width of the tile GEMM (0 = default)
     int gemm_interleave = 1;              // option "gemm_interleave": interleaved slot assignment of the tile GEMM (L2 locality)

@@ -27,7 +27,7 @@ for cfg, N, Ns, W in cases:
     if os.environ.get("GPX_LOOKAHEAD"): h.set_option("lookahead", int(os.environ["GPX_LOOKAHEAD"]))
     for rep in range(2):
         dist.barrier(); t0 = time.time()
-        h.fit(c['X'], c['Y'], kid, kk.get('variance', 1.0), ls, kw['noise_prior'])
+        h.fit(c['X'], c['Y'], kid, kk.get('variance', 1.0), ls, kw['noise_prior'], ARD=kk.get('ARD', False))
         dist.barrier(); t1 = time.time()
         mean, var = h.predict(c['Xs'])
         dist.barrier(); t2 = time.time()

@@ -4,7 +4,10 @@ from thesis_code_b200 import _gpx, synthetic
 N = int(sys.argv[1]); W = int(sys.argv[2])
 c = synthetic.make_config("C5", N=N, Ns=256)
 kk = c['model']['kwargs']['kernel']['kwargs']
+import os
 h = _gpx.Handle(0); h.set_option("outer_tiles", W); h.set_option("trace", 1)
+for kv in filter(None, os.environ.get("GPX_OPTS", "").split(",")):
+    k, v = kv.split("="); h.set_option(k, int(v))
 for rep in range(2):
     h.fit(c['X'], c['Y'], 0, 1.0, np.array(kk['lengthscale']), 1e-2, ARD=True)
 tr = h.trace(); ph = h.phase_ms()
