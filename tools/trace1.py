@@ -15,7 +15,7 @@ nt = (N + 127) // 128
 if W == 0:   # auto panel width: recover it from the number of panels
     W = next(w for w in range(1, 65) if (nt + w - 1) // w == tr.shape[0])
 print("N", N, "W", W, "chol ms", ph['cholesky'], "TF/s", N**3/3/ph['cholesky']/1e9)
-fact = tr[:, 1] - tr[:, 0]; a = tr[:, 3] - tr[:, 2]; f = tr[:, 4] - tr[:, 3]; b = tr[:, 5] - tr[:, 4]
+fact = tr[:, 1] - tr[:, 0]; a = tr[:, 3] - tr[:, 2]; f = np.zeros_like(a); b = tr[:, 5] - tr[:, 3]   # the forward steps run on their own stream
 gaps = tr[1:, 2] - tr[:-1, 5]
 print("sum: factor %.1f (a) %.1f fwd %.1f (b) %.1f  waits-for-panel %.1f  end %.1f" % (fact.sum(), a.sum(), f.sum(), b.sum(), gaps[gaps > 0].sum(), tr[-1, 5]))
 # efficiency of (b): flops of (b) at panel p
