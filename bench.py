@@ -34,10 +34,10 @@ FP64_DMMA_PEAK_TFLOPS = 36.96   # measured on this pool's B200 with tools/fp64_p
 METRIC = "exact-GP fit+predict FP64 throughput (algorithmic N^3/3 + N^2*N* flop per fit+predict)"
 # DRAM traffic of the dominant kernel from the latest `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum of
 # one launch; profiles/): refreshed whenever the kernel changes.
-GEMM_TRAFFIC = {"dram_bytes_per_launch": 4.27e9,
-                "note": "ncu --set full capture of one trailing-update launch of the final round-2 kernel "
-                        "(profiles/r02_gemm_dmma_ncu_summary.txt): 4.27 GB DRAM for 2.9 GB algorithmic operand bytes = 1.47x "
-                        "(7% of HBM peak: the kernel is DMMA-bound; DMMA pipe 96.0% of active cycles, L2 hit rate 82%)"}
+GEMM_TRAFFIC = {"dram_bytes_per_launch": 3.62e9,
+                "note": "ncu --set full capture of one trailing-update launch of the shipped kernel "
+                        "(profiles/r02_gemm_dmma_ncu_summary.txt): 3.62 GB DRAM for 2.9 GB algorithmic operand bytes = 1.25x "
+                        "(6% of HBM peak: the kernel is DMMA-bound; DMMA pipe 96.5% of active cycles, L2 hit rate 86%)"}
 
 
 def algorithmic_flops(N, Ns):
