@@ -122,7 +122,8 @@ GPX_API int gpx_lml(gpx_t* h, double* lml, double* logdet, double* quad);
  * Ns <= 128 on a single-GPU handle takes the latency path (src/growth_model_GPR/ipopt_wrapper.py:55 and
  * src/acquisition_functions.py:38,79 predict one or a few rows at a time, by the million): persistent workspaces and a
  * pinned staging buffer (no allocation, no cudaMemGetInfo), the variance of <= 8 rows by GEMV-style forward
- * substitution (L is read once, no tensor-core tile work), the whole launch chain replayed as a CUDA graph.
+ * substitution (L is read once, no tensor-core tile work) or, once the explicit inverse of the factor exists (option
+ * "latency_inverse"), by one triangular GEMV over it; the whole launch chain replayed as a CUDA graph.
  */
 GPX_API int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int var_cols,
                 int include_noise, int mem);
@@ -183,7 +184,11 @@ GPX_API int64_t gpx_launch_count(const gpx_t* h);
  * "panel_inverse" (in-panel variance solve through the inverted W x W-tile diagonal blocks: -1 auto = predicts with >= 64 test
  * tiles on one GPU, 0 off, 1 on), "gemm_strip" (rasterisation strip width of the tile GEMM, 0 = 16), "gemm_interleave" (1,
  * default: resident CTAs walk neighbouring tile slots), "nccl_full_from_pct" (panel broadcasts switch from the low-CTA to the
- * full-width communicator at this percentage of the panels, default 72). */
+ * full-width communicator at this percentage of the panels, default 72), "latency_inverse" (explicit inverse of the factor,
+ * L^-T as a packed-upper tile matrix, for the latency path: the variance of <= 8 rows and the <= 8-point gpx_append become
+ * triangular GEMV sweeps at HBM rate instead of nt dependent substitution steps; costs N^3/3 flop and the factor's memory
+ * once per fit, appends inside the last tile keep it up to date.  -1 auto = built by the 16th small variance predict of a
+ * fit if it fits in 60 % of the free memory, 0 = never (drops a built one), 1 = at the first such predict). */
 GPX_API int gpx_set_option(gpx_t* h, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel of this handle is launched on, so that a caller can
  * bracket calls with its own CUDA events (bench.py does, via torch.cuda.ExternalStream). */

@@ -582,6 +582,78 @@ def test_small_batch_predict_latency_path(gpu_handle, graph):
     gpu_handle.set_option("predict_graph", 1)
 
 
+@pytest.mark.parametrize("graph", [1, 0])
+def test_explicit_inverse_variance_route_matches_substitution_and_oracle(gpu_handle, graph):
+    """Variance of <= 8 rows through the explicit inverse of the factor (option latency_inverse; one triangular GEMV instead
+    of nt dependent substitution steps): same numbers as the substitution route and the oracle for tile counts that are /
+    are not multiples of the panel width, a single tile, reserve rows beyond N, several outputs with the output normaliser's
+    replicated variance columns; the automatic mode builds the inverse by the 16th call; appends and refits invalidate it."""
+    h = gpu_handle
+    h.set_option("predict_graph", graph)
+    rng = np.random.RandomState(11)
+    try:
+        for N, d, O, name, ARD, W, reserve in [(100, 2, 1, "GPyRBF", False, 0, 0), (1000, 3, 1, "GPyMatern52", True, 3, 0),
+                                               (1700, 1, 1, "GPyRBF", False, 4, 700), (900, 5, 2, "GPyMatern32", True, 2, 0)]:
+            X = rng.rand(N, d); Y = np.stack([np.sin(3 * X.sum(1) + o_) for o_ in range(O)], 1) + 0.05 * rng.randn(N, O)
+            ls = rng.uniform(0.3, 1.0, d if ARD else 1)
+            h.set_option("outer_tiles", W); h.set_option("reserve_rows", reserve)
+            h.set_option("latency_inverse", 0)
+            h.fit(X, Y, _gpx.KERNEL_IDS[name], 1.2, ls, 0.02, mean_const=0.1, ARD=ARD)
+            st = o.fit(X, Y, name, 1.2, ls, ARD, 0.02, mean_const=0.1)
+            Xt = rng.rand(8, d)
+            nt = (N + 127) // 128
+            sub = {Ns: h.predict(Xt[:Ns], output_dim=O) for Ns in (1, 2, 3, 4, 5, 8)}
+            h.set_option("latency_inverse", 1)
+            for Ns in (1, 2, 3, 4, 5, 8):
+                for rep in range(2):
+                    before = h.launch_count()
+                    mean, var = h.predict(Xt[:Ns], output_dim=O)
+                    used = h.launch_count() - before
+                    assert rep == 0 and Ns == 1 or used == (5 if Ns <= 4 else 6), (N, Ns, rep, used)   # loader, K*, mean, GEMV(s), variance
+                    om, ov = o.predict(st, Xt[:Ns])
+                    assert normwise(mean, om) < TOL and normwise(var, ov[:, 0]) < TOL, (N, Ns, rep)
+                    assert np.array_equal(mean, sub[Ns][0]) and normwise(var, sub[Ns][1]) < 1e-10, (N, Ns, rep)
+            mv, vv = h.predict(Xt[:3], output_dim=O, var_cols=O)
+            assert np.array_equal(np.asarray(vv).reshape(3, -1)[:, 0], h.predict(Xt[:3], output_dim=O)[1])
+            # appends inside the last tile go through the inverse too and keep it up to date (new columns of L^-T; alpha from it)
+            Xa, Ya = X, Y
+            for k in (1, 1, 5, 3):
+                Xn = rng.rand(k, d); Yn = np.stack([np.sin(3 * Xn.sum(1) + o_) for o_ in range(O)], 1)
+                h.append(Xn, Yn)
+                Xa, Ya = np.vstack([Xa, Xn]), np.vstack([Ya, Yn])
+                sta = o.fit(Xa, Ya, name, 1.2, ls, ARD, 0.02, mean_const=0.1)
+                assert abs(h.lml()[0] - sta["lml"]) / abs(sta["lml"]) < TOL
+                alpha, _ = h.export(Xa.shape[0], O)
+                assert normwise(alpha, sta["alpha"]) < 1e-6
+                for Ns in (1, 6):
+                    before = h.launch_count()
+                    mean, var = h.predict(Xt[:Ns], output_dim=O)
+                    assert h.launch_count() - before == (5 if Ns <= 4 else 6), (N, k, Ns)   # the inverse is still in use
+                    om, ov = o.predict(sta, Xt[:Ns])
+                    assert normwise(mean, om) < TOL and normwise(var, ov[:, 0]) < TOL, (N, k, Ns)
+                mean_b, var_b = h.predict(rng.rand(300, d), output_dim=O)                    # the factor itself got the rows too
+                chk = h.selfcheck()
+                assert chk["factor_residual"] < 1e-12 and chk["solve_residual"] < 1e-8, chk
+            X, Y = Xa, Ya
+            # without the inverse an append runs the substitution chain; in automatic mode the 16th small predict rebuilds it
+            h.set_option("latency_inverse", 0); h.set_option("latency_inverse", -1)
+            Xn = rng.rand(2, d); Yn = np.stack([np.sin(3 * Xn.sum(1) + o_) for o_ in range(O)], 1)
+            h.append(Xn, Yn)
+            st2 = o.fit(np.vstack([X, Xn]), np.vstack([Y, Yn]), name, 1.2, ls, ARD, 0.02, mean_const=0.1)
+            nt2 = (X.shape[0] + 2 + 127) // 128
+            om, ov = o.predict(st2, Xt[:2])
+            counts = []
+            for call in range(18):
+                before = h.launch_count()
+                mean, var = h.predict(Xt[:2], output_dim=O)
+                counts.append(h.launch_count() - before)
+                assert normwise(mean, om) < TOL and normwise(var, ov[:, 0]) < TOL, (N, call)
+            assert counts[:15] == [4 + nt2] * 15 and counts[16:] == [5, 5], counts      # the 16th call builds the inverse
+    finally:
+        for k, v in (("predict_graph", 1), ("latency_inverse", -1), ("outer_tiles", 0), ("reserve_rows", 0)):
+            h.set_option(k, v)
+
+
 def test_empty_test_set_returns_empty_arrays():
     c = synthetic.make_config("C2", N=300, Ns=5)
     m = GPModel.from_config(c["model"]["kwargs"]); m.init(c["X"], c["Y"])

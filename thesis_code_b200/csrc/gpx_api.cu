@@ -451,6 +451,12 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "gemm_strip")) { if (value < 0 || value > 64) return fail(h, -1, "gemm_strip out of range"); h->gemm_strip = (int)value; return 0; }
     if (!strcmp(name, "reserve_rows")) { if (value < 0) return fail(h, -1, "bad reserve_rows"); h->reserve_rows = value; return 0; }
     if (!strcmp(name, "predict_graph")) { h->predict_graph = value ? 1 : 0; h->gen++; return 0; }
+    if (!strcmp(name, "latency_inverse")) {   // -1 auto, 0 off (drops a built inverse), 1 build at the first small variance predict
+        h->latency_inverse = (int)value;
+        if (value == 0 && h->finv_valid) { h->finv_valid = false; h->gen++; }
+        h->finv_failed = false;
+        return 0;
+    }
     return fail(h, -1, "unknown option %s", name);
 }
 
@@ -504,6 +510,7 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     h->cap_nt = cap_nt;
     h->gen++;   // invalidates captured predict graphs
     h->minv_valid = 0;
+    finv_invalidate(h);
     h->N = N; h->Np = Np; h->nt = nt; h->d = d; h->O = O; h->kernel_id = kernel_id; h->n_ls = n_ls;
     h->variance = variance; h->noise = noise; h->jitter = jitter; h->mean_const = mean_const;
     h->ard = ard ? 1 : 0;
@@ -533,8 +540,9 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
         // out of memory: give back everything that is only a cache or a workspace of earlier predicts / appends / larger
         // fits (they are rebuilt on demand) and try once more
         for (DevBuf* b : {&h->Tt, &h->mean_partial, &h->sp, &h->minv, &h->ywork, &h->var_partial, &h->dmean, &h->dvar, &h->Xt,
-                          &h->xtsq, &h->zkeep, &h->cache, &h->gbuf[0], &h->gbuf[1], &h->stage})
+                          &h->xtsq, &h->zkeep, &h->cache, &h->gbuf[0], &h->gbuf[1], &h->stage, &h->finv, &h->finv_partial})
             release(h, *b);
+        h->finv_layout_cap = -1;
         h->sp_key[0] = -1; h->minv_valid = 0; h->minv_layout_cap = -1; h->zkeep_valid = false;
         if ((rc = ensure(h, h->L, (size_t)(off > 0 ? off : 1) * 8))) return rc;
     }
@@ -1101,6 +1109,7 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     if (h->d > gpx_grad_max_d()) return fail(h, -1, "gpx_lml_grad supports input dimension <= %d", gpx_grad_max_d());
     GPX_CUDA(h, cudaSetDevice(h->device));
     // workspaces: Y = L^-T as an nt x nt tile matrix (in Tt), Ky^-1 packed lower, per-tile partial sums
+    if (!h->finv_valid) { release(h, h->finv); release(h, h->finv_partial); h->finv_layout_cap = -1; }   // a stale latency-path inverse
     {
         size_t fr = 0, tot = 0;
         GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));

@@ -162,6 +162,13 @@ struct gpx_handle {
     size_t pin_bytes = 0;
     struct SmallGraph { uint64_t gen; int64_t Ns; int want_var, var_cols, include_noise, nodes; cudaGraphExec_t exec; };
     std::vector<SmallGraph> graphs;
+    // explicit inverse of the factor, Y = L^-T as a packed-upper tile matrix (column J holds the tile rows 0 .. end of J's
+    // panel): the variance of <= 8 rows becomes ONE triangular GEMV over it instead of nt dependent substitution steps
+    int latency_inverse = -1;   // option "latency_inverse": -1 auto (built by the 16th small variance predict of a fit), 0 off, 1 at the first
+    bool finv_valid = false, finv_failed = false;
+    int finv_calls = 0, finv_C = 1, finv_S = 1;
+    int finv_layout_cap = -1, finv_layout_w = -1;
+    DevBuf finv, finv_coloff, finv_partial;
 
     cudaEvent_t ev[2 * GPX_NUM_PHASES];
     float phase_ms[GPX_NUM_PHASES];
@@ -352,6 +359,8 @@ int backward_solve(gpx_t* h);
 int ensure_panel_inverse(gpx_t* h, int upto_panel);
 // step-wise in-panel solve of the tile rows [i0, nb) of X against the columns [p0, p1) of P
 void trsm_inner_stepwise(gpx_t* h, TileMat X, int nb, TileMat P, int p0, int p1, int i0 = 0);   // inverted W x W-tile diagonal blocks of the panels [0, upto_panel)
+// fits / appends invalidate the explicit inverse of the factor (gpx_update.cu)
+inline void finv_invalidate(gpx_t* h) { h->finv_valid = false; h->finv_failed = false; h->finv_calls = 0; }
 int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int var_cols, int include_noise,
                       int mem);
 void gpx_launch_kbuild_rows(TileMat L, int nt, int i_first, const double* Xs, const double* xsq, int64_t N, int d,

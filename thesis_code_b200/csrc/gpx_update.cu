@@ -38,12 +38,15 @@ __global__ void __launch_bounds__(256) vec_var_kernel(const double* __restrict__
 
 // Incremental forward substitution of gpx_append: partial[(i * S + s)][o][r] = sum over the tile columns J of split s
 // (J < jend) of (L(i0 + i, J) z_o[J])[r]  -- the new tile rows against the z the fit left behind.  grid (rows, S).
+// upper = 1: the tile columns of row i0 + i start at the diagonal, J in [i0 + i, jend) -- the rows of the packed-upper
+// explicit inverse Y = L^-T times a vector.
 constexpr int kRowRhs = 8;
 __global__ void __launch_bounds__(256) row_gemv_partial_kernel(TileMat L, int i0, int jend, int S, const double* __restrict__ z,
-                                                               int64_t Np, int O, double* __restrict__ partial) {
+                                                               int64_t Np, int O, double* __restrict__ partial, int upper) {
     __shared__ double sz[kRowRhs][GPX_TILE], scratch[kRowRhs][GPX_TILE];
     const int i = blockIdx.x, sidx = blockIdx.y, tid = threadIdx.x, r = tid & 127, half = tid >> 7;
-    const int J0 = (int)((long long)jend * sidx / S), J1 = (int)((long long)jend * (sidx + 1) / S);
+    const int jlo = upper ? i0 + i : 0, jn = jend - jlo;
+    const int J0 = jlo + (int)((long long)jn * sidx / S), J1 = jlo + (int)((long long)jn * (sidx + 1) / S);
     double acc[kRowRhs];
 #pragma unroll
     for (int o = 0; o < kRowRhs; o++) acc[o] = 0.0;
@@ -77,15 +80,16 @@ __global__ void __launch_bounds__(256) row_gemv_partial_kernel(TileMat L, int i0
         if (o < O && half == 0) partial[(((int64_t)i * S + sidx) * O + o) * GPX_TILE + r] = acc[o] + scratch[o][r];
 }
 
-// b[o][(i0 + i) * 128 + r] -= sum_s partial[(i * S + s)][o][r]   (fixed order)
+// b[o][(i0 + i) * 128 + r] -= sum_s partial[(i * S + s)][o][r]   (fixed order; assign = 1: b = + the sum)
 __global__ void row_gemv_apply_kernel(const double* __restrict__ partial, int rows, int S, int O, int i0, int64_t Np,
-                                      double* __restrict__ b) {
+                                      double* __restrict__ b, int assign) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)rows * O * GPX_TILE) return;
     const int r = (int)(e & 127), o = (int)((e >> 7) % O), i = (int)((e >> 7) / O);
     double s = 0.0;
     for (int k = 0; k < S; k++) s += partial[(((int64_t)i * S + k) * O + o) * GPX_TILE + r];
-    b[(int64_t)o * Np + (int64_t)(i0 + i) * GPX_TILE + r] -= s;
+    double* dst = b + (int64_t)o * Np + (int64_t)(i0 + i) * GPX_TILE + r;
+    *dst = assign ? s : *dst - s;
 }
 
 // ---- GEMV-style append of k <= 8 observations that fit into the partially filled last tile -----------------------------
@@ -103,6 +107,7 @@ struct AppendArgs {
     double* zy;             // [O][Np]  (zkeep)
     const double* resid;    // [O][Np]
     double* linv_tile;      // inverted diagonal tile of the last tile column
+    double* cinv_out;       // null, or kAppMax x kAppMax: C^-1 (lower) for the update of the explicit inverse of the factor
     int* info;
     int64_t N0, Np;
     int k, d, O, t0, r0, kernel_id;
@@ -167,6 +172,9 @@ __global__ void __launch_bounds__(1024) append_finish_kernel(TileMat L, AppendAr
                 for (int m = q; m < p; m++) s -= C[p][m] * Ci[m][q];
                 Ci[p][q] = s / C[p][p];
             }
+        if (a.cinv_out)
+            for (int p = 0; p < kAppMax; p++)
+                for (int q = 0; q < kAppMax; q++) a.cinv_out[p * kAppMax + q] = (p < k && q <= p) ? Ci[p][q] : 0.0;
         for (int p = 0; p < k; p++)       // z_y of the new rows
             for (int o = 0; o < a.O; o++) {
                 double s = 0.0;
@@ -344,6 +352,7 @@ size_t moments_smem(int d) { return (size_t)(256 + d + 256 * d) * sizeof(double)
 struct SmallWs {   // views into h->sp (one allocation, re-made when cap_nt / d / O change)
     double *Xin, *Xt, *xtsq, *mean_partial, *b, *z, *mean, *var;
 };
+constexpr int kFinvAutoCalls = 16;
 constexpr int kVecRows = 8;   // variance of <= 8 rows: GEMV-style substitution; above: one tile row through the DMMA solve
 
 SmallWs small_views(gpx_t* h) {
@@ -380,6 +389,200 @@ int small_workspace(gpx_t* h) {
     return 0;
 }
 
+
+// ---- explicit inverse of the factor for the 1..8-row variance --------------------------------------------------------
+// Y = L^-T is kept as a packed-upper tile matrix; v = L^-1 k* is then v_J = sum_{i <= J} Y(i, J)^T k*_i: no dependent chain,
+// every tile is read exactly once, at HBM rate.  grid (nt, S): CTA (J, c) sums the tile rows i in [c C, min((c + 1) C, J + 1)).
+// Thread map: warp w owns the column chunks w and w + 8 of the tile, lane = rsub * 4 + kp reads the double2 (r, 2 kp) of
+// the rows r = 8 r8 + rsub -- a warp load is 512 contiguous bytes -- and the row sum is finished with three shuffles.
+template <int RHS>
+__global__ void __launch_bounds__(256) finv_gemv_kernel(TileMat Y, int C, int S, const double* __restrict__ b, int64_t Np,
+                                                        double* __restrict__ partial) {
+    const int J = blockIdx.x, c = blockIdx.y, i0 = c * C;
+    if (i0 > J) return;
+    const int i1 = (i0 + C < J + 1) ? i0 + C : J + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rsub = lane >> 2, kp = lane & 3;
+    double acc[2][RHS][2];
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+        for (int q = 0; q < RHS; q++) acc[hh][q][0] = acc[hh][q][1] = 0.0;
+    for (int i = i0; i < i1; i++) {
+        const double* tp = tile_ptr(Y, i, J) + rsub * 8 + 2 * kp;
+        const double* bi = b + (int64_t)i * GPX_TILE + rsub;
+#pragma unroll 4
+        for (int r8 = 0; r8 < 16; r8++) {
+            const double2 t0 = __ldcs(reinterpret_cast<const double2*>(tp + warp * 1024 + r8 * 64));
+            const double2 t1 = __ldcs(reinterpret_cast<const double2*>(tp + (warp + 8) * 1024 + r8 * 64));
+#pragma unroll
+            for (int q = 0; q < RHS; q++) {
+                const double bv = __ldg(bi + (int64_t)q * Np + r8 * 8);
+                acc[0][q][0] = fma(t0.x, bv, acc[0][q][0]);
+                acc[0][q][1] = fma(t0.y, bv, acc[0][q][1]);
+                acc[1][q][0] = fma(t1.x, bv, acc[1][q][0]);
+                acc[1][q][1] = fma(t1.y, bv, acc[1][q][1]);
+            }
+        }
+    }
+    double* out = partial + ((int64_t)J * S + c) * RHS * GPX_TILE;
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+        for (int q = 0; q < RHS; q++) {
+            double x = acc[hh][q][0], y = acc[hh][q][1];
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+                x += __shfl_xor_sync(0xffffffffu, x, off);
+                y += __shfl_xor_sync(0xffffffffu, y, off);
+            }
+            if (rsub == 0) *reinterpret_cast<double2*>(out + q * GPX_TILE + (warp + 8 * hh) * 8 + 2 * kp) = make_double2(x, y);
+        }
+}
+
+// var[s] = prior - sum_J | sum_c partial(J, c)[s] |^2 : one CTA per test row, fixed order (deterministic)
+// (more than 4 right-hand sides are computed as two groups of 4: partial + group * gstride)
+__global__ void __launch_bounds__(1024) finv_var_kernel(const double* __restrict__ partial, int nt, int C, int S, int rhs,
+                                                        int64_t gstride, double prior, const double* __restrict__ ystats,
+                                                        int var_cols, double* __restrict__ var) {
+    __shared__ double red[32];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    partial += (int64_t)(s / rhs) * gstride;
+    const int sl = s % rhs;
+    double a = 0.0;
+    for (int e = tid; e < nt * GPX_TILE; e += 1024) {
+        const int J = e >> 7, col = e & 127, nc = J / C + 1;
+        const double* p = partial + (((int64_t)J * S) * rhs + sl) * GPX_TILE + col;
+        double v = 0.0;
+        for (int c = 0; c < nc; c++) v += p[(int64_t)c * rhs * GPX_TILE];
+        a = fma(v, v, a);
+    }
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if ((tid & 31) == 0) red[tid >> 5] = a;
+    __syncthreads();
+    if (tid < var_cols) {
+        double t = 0.0;
+        for (int w = 0; w < 32; w++) t += red[w];
+        const double v = prior - t;
+        const double sd = ystats ? ystats[var_cols + tid] : 1.0;
+        var[(int64_t)s * var_cols + tid] = ystats ? v * (sd * sd) : v;
+    }
+}
+
+// z[s][J * 128 + col] = sum_c partial(J, c)[s][col]: the vectors L^-1 b themselves (gpx_append).  grid (nt, nvec), 128 threads
+__global__ void finv_collect_kernel(const double* __restrict__ partial, int C, int S, int rhs, int64_t gstride, int64_t Np,
+                                    double* __restrict__ z) {
+    const int J = blockIdx.x, s = blockIdx.y, col = threadIdx.x, nc = J / C + 1;
+    const double* p = partial + (int64_t)(s / rhs) * gstride + (((int64_t)J * S) * rhs + (s % rhs)) * GPX_TILE + col;
+    double v = 0.0;
+    for (int c = 0; c < nc; c++) v += p[(int64_t)c * rhs * GPX_TILE];
+    z[(int64_t)s * Np + (int64_t)J * GPX_TILE + col] = v;
+}
+
+// gpx_append of k <= 8 rows inside the last tile keeps the explicit inverse up to date: with L_new = [L 0; Z^T C],
+//   Y_new = L_new^-T = [ Y  -U C^-T ; 0  C^-T ],  U = Y Z  (the rows of Y times the new rows of L, row_gemv kernels),
+// i.e. k new columns inside the last tile column t0 (local columns r0 .. r0 + k - 1).  One thread per row j < N0 + k.
+__global__ void finv_append_cols_kernel(TileMat Y, const double* __restrict__ U, const double* __restrict__ cinv, int64_t N0,
+                                        int64_t Np, int t0, int r0, int k) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N0 + k) return;
+    double* tp = tile_ptr(Y, (int)(j >> 7), t0);
+    const int r = (int)(j & 127);
+    for (int p = 0; p < k; p++) {
+        double v = 0.0;
+        if (j < N0) { for (int q = 0; q <= p; q++) v = fma(-U[(int64_t)q * Np + j], cinv[p * kAppMax + q], v); }
+        else { const int q = (int)(j - N0); v = q <= p ? cinv[p * kAppMax + q] : 0.0; }
+        tp[gpx_tile_idx(r, r0 + p)] = v;
+    }
+}
+
+// diagonal tiles of a zeroed tile matrix <- I
+__global__ void diag_identity_kernel(TileMat T) {
+    double* tp = tile_ptr(T, blockIdx.x, blockIdx.x);
+    if (threadIdx.x < GPX_TILE) tp[gpx_tile_idx(threadIdx.x, threadIdx.x)] = 1.0;
+    gpx_publish_for_async_proxy();
+}
+
+inline TileMat finvmat(gpx_t* h) { return TileMat{ptr<double>(h->finv), ptr<int64_t>(h->finv_coloff), 0}; }
+// right-hand sides per launch: 1, 2 or 4; 5..8 vectors run as two launches of 4 (the 8-wide instantiation needs 96 registers
+// and measured 3.5x slower per tile than the 4-wide one: too few loads in flight)
+inline int finv_rhs(int64_t nvec) { return nvec <= 1 ? 1 : nvec <= 2 ? 2 : 4; }
+inline int64_t finv_gstride(const gpx_t* h, int rhs) { return (int64_t)h->nt * h->finv_S * rhs * GPX_TILE; }
+// partial sums of Y^T b for nvec <= 8 vectors b[q][Np]; returns the number of launches
+int launch_finv_gemv(gpx_t* h, int nvec, const double* b, cudaStream_t st) {
+    const TileMat Y = finvmat(h);
+    const dim3 grid(h->nt, h->nt / h->finv_C + 1);
+    const int rhs = finv_rhs(nvec), groups = (nvec + rhs - 1) / rhs;
+    for (int g = 0; g < groups; g++) {
+        double* part = ptr<double>(h->finv_partial) + g * finv_gstride(h, rhs);
+        const double* bg = b + (int64_t)g * rhs * h->Np;
+        if (rhs == 1) finv_gemv_kernel<1><<<grid, 256, 0, st>>>(Y, h->finv_C, h->finv_S, bg, h->Np, part);
+        else if (rhs == 2) finv_gemv_kernel<2><<<grid, 256, 0, st>>>(Y, h->finv_C, h->finv_S, bg, h->Np, part);
+        else finv_gemv_kernel<4><<<grid, 256, 0, st>>>(Y, h->finv_C, h->finv_S, bg, h->Np, part);
+    }
+    return groups;
+}
+// out[o][*] = Y v_o for nrhs <= 8 vectors (the rows of the packed-upper inverse times a vector): two launches
+int finv_row_apply(gpx_t* h, const double* v, int nrhs, double* out, cudaStream_t st) {
+    const int nt = h->nt;
+    int S2 = (8 * h->num_sms + nt - 1) / nt;
+    if (S2 > nt) S2 = nt;
+    if (S2 > h->finv_S) S2 = h->finv_S;    // the partial-sum buffer is sized for cap_nt * finv_S * 8 vectors
+    row_gemv_partial_kernel<<<dim3(nt, S2), 256, 0, st>>>(finvmat(h), 0, nt, S2, v, h->Np, nrhs, ptr<double>(h->finv_partial), 1);
+    row_gemv_apply_kernel<<<(int)(((int64_t)nt * nrhs * GPX_TILE + 255) / 256), 256, 0, st>>>(ptr<double>(h->finv_partial), nt, S2, nrhs, 0,
+                                                                                           h->Np, out, 1);
+    return 2;
+}
+
+// Build Y = L^-T with the blocked DMMA solve of the predictive variance applied to the identity (N^3/3 flop, once per fit
+// generation; the same job list as gpx_lml_grad's first step).  Running out of memory is not an error: the substitution
+// route stays in use for this fit.
+int build_factor_inverse(gpx_t* h) {
+    const int W = h->W, cap = h->cap_nt, nt = h->nt;
+    std::vector<int64_t> off(cap);
+    int64_t tiles = 0;
+    for (int c = 0; c < cap; c++) {
+        int p1 = (c / W + 1) * W;
+        if (p1 > cap) p1 = cap;
+        off[c] = tiles * GPX_TILE_ELEMS;
+        tiles += p1;
+    }
+    // tile rows per CTA: about 8 CTAs per SM over the nt (nt + 1) / 2 tiles of a full sweep, at capacity
+    const int64_t total = (int64_t)cap * (cap + 1) / 2;
+    int C = (int)((total + 8LL * h->num_sms - 1) / (8LL * h->num_sms));
+    if (C < 1) C = 1;
+    const int S = (cap - 1) / C + 1;
+    const size_t part_bytes = (size_t)cap * S * kVecRows * GPX_TILE * 8;
+    if (h->finv_layout_cap != cap || h->finv_layout_w != W || !h->finv.p) {
+        release(h, h->finv); release(h, h->finv_partial);
+        size_t fr = 0, tot = 0;
+        GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
+        const double need = (double)tiles * GPX_TILE_BYTES + (double)part_bytes;
+        if (need > 0.6 * (double)fr || ensure(h, h->finv, (size_t)tiles * GPX_TILE_BYTES) || ensure(h, h->finv_partial, part_bytes) ||
+            ensure(h, h->finv_coloff, (size_t)cap * 8)) {
+            release(h, h->finv); release(h, h->finv_partial);
+            h->finv_layout_cap = -1;
+            h->finv_failed = true;
+            h->err.clear();
+            return 0;
+        }
+        GPX_CUDA(h, cudaMemcpyAsync(h->finv_coloff.p, off.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, h->st));
+        GPX_CUDA(h, cudaStreamSynchronize(h->st));   // off is a host temporary
+        h->finv_layout_cap = cap; h->finv_layout_w = W;
+    }
+    h->finv_C = C; h->finv_S = S;
+    TileMat Y{ptr<double>(h->finv), ptr<int64_t>(h->finv_coloff), 0};
+    GPX_CUDA(h, cudaMemsetAsync(h->finv.p, 0, (size_t)tiles * GPX_TILE_BYTES, h->st));
+    diag_identity_kernel<<<nt, GPX_TILE, 0, h->st>>>(Y);
+    h->launches++;
+    const int keep = h->minv_active;
+    h->minv_active = 0;
+    for (int p = 0; p < h->npanels; p++) var_trsm_panel(h, Y, nt, lmat(h), p, true);
+    h->minv_active = keep;
+    h->finv_valid = true;
+    h->gen++;   // captured predict graphs of this fit still run the substitution chain
+    return 0;
+}
+
 // the graph-capturable part of the latency path: loader -> K* (+ mean partials, + right-hand-side vectors) -> mean
 // -> [forward substitution -> variance].  Returns the number of kernels launched.
 int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_cols, int include_noise, cudaStream_t st) {
@@ -392,11 +595,18 @@ int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_c
                       want_var ? w.b : nullptr, (int)Ns); n++;
     gpx_launch_mean_reduce(w.mean_partial, 1, nt, O, h->mean_const, y_stats(h), w.mean, 0, Ns, st); n++;
     if (want_var) {
-        for (int J = 0; J < nt; J++) {
-            gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, w.b, w.z, Np, (int)Ns, 2 * h->num_sms, st); n++;
-        }
         const double prior = h->variance + (include_noise ? h->noise : 0.0);
-        vec_var_kernel<<<(int)Ns, 256, 0, st>>>(w.z, (int64_t)nt * GPX_TILE, Np, prior, y_stats(h), var_cols, w.var); n++;
+        if (h->finv_valid) {   // explicit inverse: one triangular GEMV, no dependent chain
+            const int rhs = finv_rhs(Ns);
+            n += launch_finv_gemv(h, (int)Ns, w.b, st);
+            finv_var_kernel<<<(int)Ns, 1024, 0, st>>>(ptr<double>(h->finv_partial), nt, h->finv_C, h->finv_S, rhs, finv_gstride(h, rhs),
+                                                     prior, y_stats(h), var_cols, w.var); n++;
+        } else {
+            for (int J = 0; J < nt; J++) {
+                gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, w.b, w.z, Np, (int)Ns, 2 * h->num_sms, st); n++;
+            }
+            vec_var_kernel<<<(int)Ns, 256, 0, st>>>(w.z, (int64_t)nt * GPX_TILE, Np, prior, y_stats(h), var_cols, w.var); n++;
+        }
     }
     return n;
 }
@@ -454,6 +664,7 @@ int relayout(gpx_t* h, int new_cap) {
     h->cap_nt = new_cap;
     h->Np = newNp;
     h->gen++;
+    finv_invalidate(h);
     return 0;
 }
 
@@ -509,21 +720,43 @@ static int append_vec(gpx_t* h, const double* Xn, int64_t k, const double* Yn, i
     resid_append_kernel<<<(int)((k * O + 255) / 256), 256, 0, st>>>(dY, k, O, h->mean_const, ptr<double>(h->resid), Np, N0, k);
     gpx_launch_kcross(TileMat{nullptr, nullptr, 0}, 1, 1, nt, w.Xt, w.xtsq, k, ptr<double>(h->Xs), ptr<double>(h->xsq), N0, d,
                       h->kernel_id, h->variance, h->rdiv, nullptr, 0, Np, nullptr, st, w.b, (int)k);
-    for (int J = 0; J < nt; J++)
-        gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, w.b, w.z, Np, (int)k, 2 * h->num_sms, st);
+    // forward substitutions z_a = L^-1 k(X, x_new_a): one triangular GEMV when the explicit inverse of the factor is there
+    // (it is then kept up to date below, and alpha comes from it too: no dependent chain at all), else nt substitution steps
+    const bool use_finv = h->finv_valid && h->finv_layout_cap == h->cap_nt;
+    double* cinv = w.mean;   // kAppMax^2 <= 128 * O doubles of scratch
+    if (use_finv) {
+        const int rhs = finv_rhs(k);
+        h->launches += launch_finv_gemv(h, (int)k, w.b, st) + 1;
+        finv_collect_kernel<<<dim3(nt, (int)k), GPX_TILE, 0, st>>>(ptr<double>(h->finv_partial), h->finv_C, h->finv_S, rhs,
+                                                                  finv_gstride(h, rhs), Np, w.z);
+    } else {
+        for (int J = 0; J < nt; J++)
+            gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, w.b, w.z, Np, (int)k, 2 * h->num_sms, st);
+        h->launches += nt;
+    }
     AppendArgs a{};
     a.z = w.z; a.xt = w.Xt; a.xtsq = w.xtsq; a.zy = ptr<double>(h->zkeep); a.resid = ptr<double>(h->resid);
     a.linv_tile = ptr<double>(h->linv) + (int64_t)t0 * GPX_TILE_ELEMS; a.info = ptr<int>(h->info);
+    a.cinv_out = use_finv ? cinv : nullptr;
     a.N0 = N0; a.Np = Np; a.k = (int)k; a.d = d; a.O = O; a.t0 = t0; a.r0 = r0; a.kernel_id = h->kernel_id;
     a.variance = h->variance; a.rdiv = h->rdiv; a.diag_add = h->noise + h->jitter;
     append_finish_kernel<<<1, 1024, 0, st>>>(lmat(h), a);
-    h->launches += 3 + nt;
+    h->launches += 3;
     h->N = N0 + k;
     h->gen++;
     if (h->minv_valid > t0 / W) h->minv_valid = t0 / W;
-    // alpha: backward substitution over the whole factor (it consumes its right-hand side: a copy of the kept z), then the LML
-    GPX_CUDA(h, cudaMemcpyAsync(h->work2.p, h->zkeep.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
-    rc = backward_solve(h);
+    if (use_finv) {
+        // the k new columns of Y = L^-T (U = Y Z lands in w.b), then alpha = L^-T z_y = Y z_y
+        h->launches += finv_row_apply(h, w.z, (int)k, w.b, st) + 1;
+        finv_append_cols_kernel<<<(int)((N0 + k + 255) / 256), 256, 0, st>>>(finvmat(h), w.b, cinv, N0, Np, t0, r0, (int)k);
+        h->launches += finv_row_apply(h, ptr<double>(h->zkeep), O, ptr<double>(h->alpha), st);
+        rc = 0;
+    } else {
+        finv_invalidate(h);
+        // alpha: backward substitution over the whole factor (it consumes its right-hand side: a copy of the kept z), then the LML
+        GPX_CUDA(h, cudaMemcpyAsync(h->work2.p, h->zkeep.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
+        rc = backward_solve(h);
+    }
     gpx_launch_lml(ptr<double>(h->linv), ptr<double>(h->alpha), ptr<double>(h->resid), (int64_t)nt * GPX_TILE, Np, O, ptr<double>(h->scal), st);
     h->launches++;
     double hs[2] = {0, 0};
@@ -536,6 +769,7 @@ static int append_vec(gpx_t* h, const double* Xn, int64_t k, const double* Yn, i
     if (e != cudaSuccess) return fail(h, -2, "CUDA error during append: %s", cudaGetErrorString(e));
     if (hinfo != 0) {
         h->zkeep_valid = false;
+        finv_invalidate(h);
         fail(h, hinfo, "append: Ky is not positive definite: non-positive pivot at row %d", hinfo);
         return hinfo;
     }
@@ -564,6 +798,14 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
         GPX_CUDA(h, cudaMemcpyAsync(w.Xin, Xs, (size_t)Ns * d * 8, cudaMemcpyDeviceToDevice, st));
     }
     const bool want_var = var != nullptr;
+    if (want_var && Ns <= kVecRows && !h->finv_valid && !h->finv_failed && h->latency_inverse != 0) {
+        // the acquisition / IPOPT loops predict one row at a time, thousands of times per fit: after a few such calls (or at
+        // the first with latency_inverse = 1) pay N^3/3 flop once for the explicit inverse of the factor
+        h->finv_calls++;
+        if (h->latency_inverse > 0 || h->finv_calls >= kFinvAutoCalls) {
+            if ((rc = build_factor_inverse(h))) return rc;
+        }
+    }
     if (!want_var || Ns <= kVecRows) {
         if (h->predict_graph) {
             // replay (or capture once per fit generation and shape) the whole launch chain as one CUDA graph
@@ -689,6 +931,7 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     h->launches++;
     h->N = N1; h->nt = nt1; h->npanels = (nt1 + W - 1) / W;
     h->gen++;
+    finv_invalidate(h);
     GPX_CUDA(h, cudaMemsetAsync(h->info.p, 0, 64, st));
     // 1. the new rows of Ky (tile rows t0 .. nt1-1; a partially filled tile row t0 is rebuilt whole)
     gpx_launch_kbuild_rows(lmat(h), nt1, t0, ptr<double>(h->Xs), ptr<double>(h->xsq), N1, d, h->kernel_id, h->variance, h->rdiv,
@@ -742,9 +985,9 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
         if (S > t0) S = t0;
         if ((rc = ensure(h, h->var_partial, (size_t)rows * S * O * GPX_TILE * 8))) { release(h, stageY); return rc; }
         GPX_CUDA(h, cudaMemcpyAsync(h->work2.p, h->zkeep.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
-        row_gemv_partial_kernel<<<dim3(rows, S), 256, 0, st>>>(L, t0, t0, S, ptr<double>(h->work2), Np, O, ptr<double>(h->var_partial));
+        row_gemv_partial_kernel<<<dim3(rows, S), 256, 0, st>>>(L, t0, t0, S, ptr<double>(h->work2), Np, O, ptr<double>(h->var_partial), 0);
         row_gemv_apply_kernel<<<(int)(((int64_t)rows * O * GPX_TILE + 255) / 256), 256, 0, st>>>(ptr<double>(h->var_partial), rows, S, O, t0, Np,
-                                                                                              ptr<double>(h->work1));
+                                                                                              ptr<double>(h->work1), 0);
         h->launches += 2;
         jfirst = t0;
     }
