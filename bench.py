@@ -193,6 +193,66 @@ def golden_parity(h, workload, N, kid, variance, ls, noise, ard, torch):
             "lml_rel": abs(lml - float(z[workload + "_lml"])) / abs(float(z[workload + "_lml"])), "gate": 1e-8}
 
 
+def other_configs_and_latency(local_rank, torch):
+    """Outside every timed region, single GPU: (i) one fit+predict of the parity configs C1-C3 at FULL size through the
+    public GPModel API with host numpy buffers (second of two runs each), so that every BASELINE config that fits one GPU has
+    a driver-run timing; (ii) the latency path of SURVEY.md section 8(f) row 3 on the fitted C2 model (N = 20000): one-row
+    predictions and one-point appends, host wall-clock medians."""
+    from thesis_code_b200 import GPModel, synthetic
+    out = {"what": "fit+predict through GPModel.init + get_statistics(full_cov=False) on host numpy arrays, second of two runs; "
+                   "latency = median host wall-clock per call on the fitted C2 model"}
+
+    def med(fn, n):
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
+    for wl in ("C1", "C2", "C3"):
+        fN = FULL_SIZES[wl][0]
+        c = synthetic.make_config(wl, N=fN + (8 if wl == "C2" else 0))
+        X, Y = c["X"][:fN], c["Y"][:fN]
+        m = GPModel.from_config(c["model"]["kwargs"])
+        m.device = local_rank
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m.init(X, Y)
+            ph = dict(m._get_handle().phase_ms())
+            mean, var = m.get_statistics(c["Xs"], full_cov=False)
+            t = time.perf_counter() - t0
+        out[wl] = {"N": fN, "d": c["d"], "N_test": c["Ns"], "fit_predict_sec": t,
+                   "tflops": algorithmic_flops(fN, c["Ns"]) / t / 1e12,
+                   "cholesky_tflops": float(fN) ** 3 / 3 / (ph["cholesky"] * 1e-3) / 1e12 if ph.get("cholesky", 0) > 0 else None,
+                   "var_min": float(var.min())}
+        if wl == "C2":
+            h2 = m._get_handle()
+            row = c["Xs"][:1]
+            lat = {"N": fN, "refit_ms": ph["kbuild"] + ph["cholesky"] + ph["solve"] + ph["lml"]}
+            h2.set_option("latency_inverse", 0)
+            m.get_statistics(row, full_cov=False); m.get_mean(row)
+            lat["mean_only_1row_us"] = med(lambda: m.get_mean(row), 50) * 1e6
+            lat["mean_var_1row_us_substitution"] = med(lambda: m.get_statistics(row, full_cov=False), 20) * 1e6
+            h2.set_option("latency_inverse", 1)
+            t0 = time.perf_counter(); m.get_statistics(row, full_cov=False); lat["inverse_build_ms"] = (time.perf_counter() - t0) * 1e3
+            lat["mean_var_1row_us_inverse"] = med(lambda: m.get_statistics(row, full_cov=False), 100) * 1e6
+            ts = []
+            for i in range(4):
+                t0 = time.perf_counter(); m.add_observations(c["X"][fN + i:fN + i + 1], c["Y"][fN + i:fN + i + 1]); ts.append(time.perf_counter() - t0)
+            lat["append_1pt_ms_inverse"] = float(np.median(ts)) * 1e3
+            h2.set_option("latency_inverse", 0)
+            ts = []
+            for i in range(4, 8):
+                t0 = time.perf_counter(); m.add_observations(c["X"][fN + i:fN + i + 1], c["Y"][fN + i:fN + i + 1]); ts.append(time.perf_counter() - t0)
+            lat["append_1pt_ms_substitution"] = float(np.median(ts)) * 1e3
+            out["latency_C2"] = lat
+        m._handle.close()
+        m._handle = None
+    return out
+
+
 def main():
     t_proc = time.perf_counter()
     ap = argparse.ArgumentParser()
@@ -205,6 +265,7 @@ def main():
     ap.add_argument("--Ns", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the untimed C1-C3 / latency-path block of the 1-GPU line")
     ap.add_argument("--trace", action="store_true", help="one extra (untimed) fit with the per-panel timeline of the Cholesky")
     ap.add_argument("--budget-s", type=float, default=float(os.environ.get("GPX_BENCH_BUDGET_S", "600")),
                     help="wall-clock budget of the whole run: the number of full-size timed steps is cut to fit it")
@@ -287,7 +348,8 @@ def main():
     e2e_steps = 1 if t_full > 20.0 else max(1, min(args.steps, 2))
     cpu_reserve = 0.0 if (args.no_cpu_baseline or rank != 0) else 25.0
     check_reserve = 0.0 if args.no_check else 0.15 * t_full + 10.0
-    left = args.budget_s - (time.perf_counter() - t_proc) - e2e_steps * 1.05 * t_full - cpu_reserve - check_reserve - 20.0
+    extras_reserve = 25.0 if (world == 1 and not args.no_extras) else 0.0
+    left = args.budget_s - (time.perf_counter() - t_proc) - e2e_steps * 1.05 * t_full - cpu_reserve - check_reserve - extras_reserve - 20.0
     steps = int(agree(max(1, min(args.steps, int(left / t_full))), dist.ReduceOp.MIN if dist is not None else None))
 
     h.gemm_stats()
@@ -398,6 +460,14 @@ def main():
                 "traffic_note": GEMM_TRAFFIC["note"],
                 "kernel_share_of_step": gemm_ms / ms_total if ms_total > 0 else None}
 
+    # ---- the other single-GPU configs and the latency path (untimed extras) ----------------------------------------------
+    extras = None
+    if world == 1 and not args.no_extras:
+        try:
+            extras = other_configs_and_latency(local_rank, torch)
+        except Exception as e:     # never lose the headline line to an extra
+            extras = {"error": repr(e)}
+
     # ---- CPU baseline: oracle port on a bounded sample ------------------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline:
@@ -425,7 +495,7 @@ def main():
             "backward_solve_gbs": (8.0 * N * (N + 1) / 2 / max(world, 1)) / (phases["solve"] * 1e-3) / 1e9,
             "kstar_gevals_per_s": (float(N) * Ns / max(world, 1)) / (phases["predict_kstar"] * 1e-3) / 1e9 if phases.get("predict_kstar", 0) > 0 else None,
             "hbm_peak_gbs": peaks.get("hbm_gbs"),
-            "roofline": roofline, "cpu_baseline": cpu, "check": check, "trace": trace_summary,
+            "roofline": roofline, "cpu_baseline": cpu, "check": check, "trace": trace_summary, "other_configs": extras,
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": "GPModel.init(X, Y) + get_statistics(Xtest, full_cov=False) on numpy arrays"},
