@@ -229,6 +229,13 @@ def other_configs_and_latency(local_rank, torch):
                    "var_min": float(var.min())}
         if wl == "C2":
             h2 = m._get_handle()
+            # one optimiser evaluation of do_optimize=True: the fit above + the LML gradient (L^-T by the
+            # DMMA triangular solve, Ky^-1 = L^-T L^-1, then the tile-wise reduction against dK/dtheta): N^3 flop in total
+            for _ in range(2):
+                t0 = time.perf_counter(); g = h2.lml_grad(m.kernel.lengthscale.size); tg = time.perf_counter() - t0
+            fit_s = (ph["kbuild"] + ph["cholesky"] + ph["solve"] + ph["lml"]) * 1e-3
+            out["optimizer_eval_C2"] = {"N": fN, "params": int(len(g)), "fit_ms": fit_s * 1e3, "lml_grad_ms": tg * 1e3,
+                                        "tflops": float(fN) ** 3 / (fit_s + tg) / 1e12}
             row = c["Xs"][:1]
             lat = {"N": fN, "refit_ms": ph["kbuild"] + ph["cholesky"] + ph["solve"] + ph["lml"]}
             h2.set_option("latency_inverse", 0)

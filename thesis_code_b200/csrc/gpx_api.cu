@@ -379,8 +379,9 @@ void gpx_destroy(gpx_t* h) {
                      &h->work1, &h->work2, &h->alpha, &h->scal, &h->info, &h->stage, &h->gbuf[0], &h->gbuf[1], &h->cache,
                      &h->ucoloff, &h->Tt,
                      &h->tt_coloff, &h->Xt, &h->xtsq, &h->mean_partial, &h->dmean, &h->dvar, &h->sp, &h->xstats, &h->ystats, &h->var_partial, &h->minv, &h->minv_coloff,
-                     &h->ywork, &h->ywork_coloff, &h->zkeep};
+                     &h->ywork, &h->ywork_coloff, &h->zkeep, &h->finv, &h->finv_coloff, &h->finv_partial};
     for (DevBuf* b : all) release(h, *b);
+    release_scratch(h);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev_caller) cudaEventDestroy(h->ev_caller);
@@ -542,6 +543,7 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
         for (DevBuf* b : {&h->Tt, &h->mean_partial, &h->sp, &h->minv, &h->ywork, &h->var_partial, &h->dmean, &h->dvar, &h->Xt,
                           &h->xtsq, &h->zkeep, &h->cache, &h->gbuf[0], &h->gbuf[1], &h->stage, &h->finv, &h->finv_partial})
             release(h, *b);
+        release_scratch(h);
         h->finv_layout_cap = -1;
         h->sp_key[0] = -1; h->minv_valid = 0; h->minv_layout_cap = -1; h->zkeep_valid = false;
         if ((rc = ensure(h, h->L, (size_t)(off > 0 ? off : 1) * 8))) return rc;
@@ -625,21 +627,21 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     // inputs
     phase_begin(h, GPX_PHASE_H2D);
     const double *dX, *dY;
-    DevBuf stageY;
+    DevBuf& stageY = h->stage_y;   // persistent: a per-fit cudaMalloc + cudaFree showed in small-N optimiser loops
     if ((rc = to_device(h, X, (size_t)N * d, mem, h->stage, &dX))) return rc;
-    if ((rc = to_device(h, Y, (size_t)N * O, mem, stageY, &dY))) { release(h, stageY); return rc; }
+    if ((rc = to_device(h, Y, (size_t)N * O, mem, stageY, &dY))) return rc;
     phase_end(h, GPX_PHASE_H2D);
 
     // K-build: only the owned panels' columns
     phase_begin(h, GPX_PHASE_KBUILD);
     // fused NormalizerModel: column means / population stds of the raw X and Y, computed here and applied by the loaders
     if (h->fit_norm_x) {
-        if ((rc = ensure(h, h->xstats, (size_t)2 * d * 8))) { release(h, stageY); return rc; }
+        if ((rc = ensure(h, h->xstats, (size_t)2 * d * 8))) return rc;
         gpx_launch_col_stats(dX, N, d, ptr<double>(h->xstats), h->st);
         h->launches++;
     }
     if (h->fit_norm_y) {
-        if ((rc = ensure(h, h->ystats, (size_t)2 * O * 8))) { release(h, stageY); return rc; }
+        if ((rc = ensure(h, h->ystats, (size_t)2 * O * 8))) return rc;
         gpx_launch_col_stats(dY, N, O, ptr<double>(h->ystats), h->st);
         h->launches++;
     }
@@ -701,7 +703,6 @@ int gpx_fit(gpx_t* h, const double* X, int64_t N, int d, const double* Y, int O,
     cudaError_t e = cudaStreamSynchronize(h->st);
     cudaError_t e2 = cudaStreamSynchronize(h->st_f);
     cudaError_t e3 = cudaStreamSynchronize(h->st_c);
-    release(h, stageY);
     if (rc) return rc;
     if (e == cudaSuccess) e = e2;
     if (e == cudaSuccess) e = e3;
@@ -1046,8 +1047,8 @@ int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double
     int rc;
     const double* dXs;
     if ((rc = to_device(h, Xs, (size_t)Ns * d, mem, h->stage, &dXs))) return rc;
-    DevBuf dm, dc, covt, covoff;
-    auto cleanup = [&]() { for (DevBuf* b : {&dm, &dc, &covt, &covoff}) release(h, *b); };
+    DevBuf &dm = h->c_dm, &dc = h->c_dc, &covt = h->c_covt, &covoff = h->c_covoff;   // kept between calls
+    auto cleanup = [&]() {};
     double* dmean = mean;
     double* dcov = cov;
     if (mem == GPX_MEM_HOST) {
@@ -1113,13 +1114,24 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     {
         size_t fr = 0, tot = 0;
         GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
-        fr += h->Tt.bytes;
+        fr += h->Tt.bytes + h->g_kinv.bytes;
         double need = ((double)nt * nt + (double)nt * (nt + 1) / 2) * GPX_TILE_BYTES;
+        if (need > 0.9 * (double)fr && h->finv.p) {   // the latency path's inverse is only a cache: give it back
+            release(h, h->finv); release(h, h->finv_partial);
+            h->finv_layout_cap = -1;
+            if (h->finv_valid) { h->finv_valid = false; h->gen++; }
+            GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
+            fr += h->Tt.bytes + h->g_kinv.bytes;
+        }
         if (need > 0.9 * (double)fr) return fail(h, -3, "gpx_lml_grad needs %.1f GB of workspace (N too large for one GPU)", need / 1e9);
     }
     int rc;
-    DevBuf kinv, kinv_off, partial, gout;
-    auto cleanup = [&]() { for (DevBuf* b : {&kinv, &kinv_off, &partial, &gout}) release(h, *b); };
+    DevBuf &kinv = h->g_kinv, &kinv_off = h->g_kinv_off, &partial = h->g_partial, &gout = h->g_out;   // kept between calls
+    auto cleanup = [&]() {};
+    // stage timing (GPX_GRAD_TRACE=1 prints it): development aid
+    static const bool trace = getenv("GPX_GRAD_TRACE") != nullptr;
+    cudaEvent_t tev[6] = {};
+    auto mark = [&](int i) { if (trace) { if (!tev[i]) cudaEventCreate(&tev[i]); cudaEventRecord(tev[i], h->st); } };
     std::vector<int64_t> tc(nt), kc(nt);
     int64_t o = 0;
     for (int c = 0; c < nt; c++) { tc[c] = (int64_t)c * nt * GPX_TILE_ELEMS; kc[c] = o; o += (int64_t)(nt - c) * GPX_TILE_ELEMS; }
@@ -1132,9 +1144,12 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     TileMat Y{ptr<double>(h->Tt), ptr<int64_t>(h->tt_coloff), 0};
     TileMat Ki{ptr<double>(kinv), ptr<int64_t>(kinv_off), 1};
     // 1. Y = L^-T : solve Y L^T = I with the blocked DMMA solve of the variance path (upper triangular rows only)
+    mark(0);
     gpx_launch_identity_tiles(Y, nt, h->st);
     h->launches++;
+    mark(1);
     for (int p = 0; p < h->npanels; p++) var_trsm_panel(h, Y, nt, lmat(h), p, true);
+    mark(2);
     // 2. Ky^-1 = Y Y^T (lower tiles; Y(I,K) = 0 for K < I, so the contraction starts at the row group's first tile)
     const int RG = 8;
     for (int I0 = 0; I0 < nt; I0 += RG) {
@@ -1145,11 +1160,21 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
         g.k0 = I0; g.k1 = nt; g.bdiag = 0; g.overwrite = 1;
         gemm(h, g, h->st);
     }
+    mark(3);
     // 3. dLML/dtheta = sum W .* dK/dtheta
     gpx_launch_lml_grad(Ki, nt, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, h->d, h->kernel_id, h->variance, h->rdiv,
                         ptr<double>(h->ls), n_ls, ptr<double>(h->alpha), h->O, h->Np, ptr<double>(partial),
                         ptr<double>(gout), h->st);
     h->launches += 3;
+    mark(4);
+    if (trace) {
+        cudaStreamSynchronize(h->st);
+        float ms[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ms[i], tev[i], tev[i + 1]);
+        fprintf(stderr, "[gpx_lml_grad] N=%lld identity %.2f ms, Y = L^-T %.2f ms, Ky^-1 = Y Y^T %.2f ms, gradient tiles %.2f ms\n",
+                (long long)h->N, ms[0], ms[1], ms[2], ms[3]);
+        for (auto& e : tev) if (e) cudaEventDestroy(e);
+    }
     std::vector<double> hg(stride + 1);
     cudaError_t e = cudaMemcpyAsync(hg.data(), gout.p, (size_t)(stride + 1) * 8, cudaMemcpyDeviceToHost, h->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);

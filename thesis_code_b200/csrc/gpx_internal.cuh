@@ -140,6 +140,10 @@ struct gpx_handle {
 
     DevBuf Xs, xsq, ls, L, linv, coloff, vcoloff, linv_coloff, resid, work1, work2, alpha, scal, info;
     DevBuf stage;
+    // persistent scratch of the calls an optimiser / acquisition loop repeats (cudaMalloc + cudaFree of the gradient's
+    // workspaces cost 3x the device time of the gradient itself at N = 20000, 10x at N = 1000): Y staging of fit / append,
+    // gpx_lml_grad (Ky^-1, offsets, per-tile partial sums, result), gpx_predict_cov, gpx_predict_moments
+    DevBuf stage_y, g_kinv, g_kinv_off, g_partial, g_out, c_dm, c_dc, c_covt, c_covoff, m_xt, m_xtsq, m_o0, m_o1, m_o2;
     DevBuf gbuf[2];                     // group buffers (world > 1): the M panels of a group, contiguous; double buffered
     int group_panels = 1;               // M: panels per delayed far update when sharded (measured: no gain from M = 4,
                                         // 2587 vs 2591 ms at 4 GPUs / N = 100k, so the simpler M = 1 is the default)
@@ -218,6 +222,13 @@ inline int ensure(gpx_t* h, DevBuf& b, size_t bytes) {
     return 0;
 }
 
+inline void release(gpx_t* h, DevBuf& b);
+// every persistent scratch buffer above (released by gpx_destroy and by the out-of-memory reclaim of gpx_fit)
+inline void release_scratch(gpx_t* h) {
+    for (DevBuf* b : {&h->stage_y, &h->g_kinv, &h->g_kinv_off, &h->g_partial, &h->g_out, &h->c_dm, &h->c_dc, &h->c_covt, &h->c_covoff,
+                      &h->m_xt, &h->m_xtsq, &h->m_o0, &h->m_o1, &h->m_o2})
+        release(h, *b);
+}
 inline void release(gpx_t* h, DevBuf& b) {
     if (b.p) {
         cudaFree(b.p);

@@ -921,9 +921,9 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     h->fitted = false;   // until the append has succeeded
     cudaStream_t st = h->st;
     const double *dX, *dY;
-    DevBuf stageY;
+    DevBuf& stageY = h->stage_y;
     if ((rc = to_device(h, Xn, (size_t)k * d, mem, h->stage, &dX))) return rc;
-    if ((rc = to_device(h, Yn, (size_t)k * O, mem, stageY, &dY))) { release(h, stageY); return rc; }
+    if ((rc = to_device(h, Yn, (size_t)k * O, mem, stageY, &dY))) return rc;
     const int64_t Np = h->Np, rows_padded = (int64_t)nt1 * GPX_TILE - N0;
     prep_inputs(h, dX, k, rows_padded, ptr<double>(h->Xs) + N0 * d, ptr<double>(h->xsq) + N0, st);
     resid_append_kernel<<<(int)((rows_padded * O + 255) / 256), 256, 0, st>>>(dY, k, O, h->mean_const, ptr<double>(h->resid), Np, N0,
@@ -945,7 +945,7 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     TileMat L = lmat(h);
     const int full_panels = t0 / W;
     if (h->minv_valid > full_panels) h->minv_valid = full_panels;
-    if (full_panels > 0 && (rc = ensure_panel_inverse(h, full_panels))) { release(h, stageY); return rc; }
+    if (full_panels > 0 && (rc = ensure_panel_inverse(h, full_panels))) return rc;
     TileMat Mi{ptr<double>(h->minv), ptr<int64_t>(h->minv_coloff), 1};
     for (int c0 = 0; c0 < t0; c0 += W) {
         const int c1 = c0 + W < t0 ? c0 + W : t0;
@@ -977,13 +977,13 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     //    previous append) left in zkeep; b_R = resid_R - sum_{J < t0} L(R, J) z_J by a split row GEMV, then the few steps inside
     //    the new block.  (More than kRowRhs outputs, or no kept z: the plain full pass.)  Backward substitution: all of L.
     GPX_CUDA(h, cudaMemcpyAsync(h->work1.p, h->resid.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
-    if ((rc = ensure(h, h->zkeep, (size_t)Np * O * 8))) { release(h, stageY); return rc; }
+    if ((rc = ensure(h, h->zkeep, (size_t)Np * O * 8))) return rc;
     int jfirst = 0;
     if (h->zkeep_valid && O <= kRowRhs && t0 > 0) {
         const int rows = nt1 - t0;
         int S = (2 * h->num_sms + rows - 1) / rows;
         if (S > t0) S = t0;
-        if ((rc = ensure(h, h->var_partial, (size_t)rows * S * O * GPX_TILE * 8))) { release(h, stageY); return rc; }
+        if ((rc = ensure(h, h->var_partial, (size_t)rows * S * O * GPX_TILE * 8))) return rc;
         GPX_CUDA(h, cudaMemcpyAsync(h->work2.p, h->zkeep.p, (size_t)Np * O * 8, cudaMemcpyDeviceToDevice, st));
         row_gemv_partial_kernel<<<dim3(rows, S), 256, 0, st>>>(L, t0, t0, S, ptr<double>(h->work2), Np, O, ptr<double>(h->var_partial), 0);
         row_gemv_apply_kernel<<<(int)(((int64_t)rows * O * GPX_TILE + 255) / 256), 256, 0, st>>>(ptr<double>(h->var_partial), rows, S, O, t0, Np,
@@ -1006,7 +1006,6 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     cudaMemcpyAsync(hs, h->scal.p, 16, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&hinfo, h->info.p, 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    release(h, stageY);
     if (rc) return rc;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, -2, "CUDA error during append: %s", cudaGetErrorString(e));
@@ -1096,8 +1095,8 @@ int gpx_predict_moments(gpx_t* h, const double* Xs, int64_t Ns, double* S0, doub
     int rc;
     const double* dXs;
     if ((rc = to_device(h, Xs, (size_t)Ns * d, mem, h->stage, &dXs))) return rc;
-    DevBuf xt, xtsq, o0, o1, o2;
-    auto cleanup = [&]() { for (DevBuf* b : {&xt, &xtsq, &o0, &o1, &o2}) release(h, *b); };
+    DevBuf &xt = h->m_xt, &xtsq = h->m_xtsq, &o0 = h->m_o0, &o1 = h->m_o1, &o2 = h->m_o2;   // kept between calls
+    auto cleanup = [&]() {};
     if ((rc = ensure(h, xt, (size_t)Ns * d * 8)) || (rc = ensure(h, xtsq, (size_t)Ns * 8))) { cleanup(); return rc; }
     double *d0 = S0, *d1 = S1, *d2 = S2;
     if (mem == GPX_MEM_HOST) {
