@@ -100,6 +100,11 @@ for bad in ("X", "theta"):
         raise SystemExit("mismatch in %s not detected" % bad)
     except RuntimeError as e:
         assert "different data or hyper-parameters" in str(e), e
+# sharded do_optimize / HMC: the ranks re-seed the global numpy RNG from one broadcast seed and then draw the same numbers
+np.random.seed(100 + rank)
+seed = gd.sync_rng(h, dist)
+draw = torch.from_numpy(np.random.normal(size=4)); ref = draw.clone(); dist.broadcast(ref, src=0)
+assert seed is not None and bool((draw == ref).all())
 # the bench's agreement on the number of timed steps: min over ranks
 t = torch.tensor([float(3 + rank)]); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 assert int(t) == 3

@@ -44,6 +44,44 @@ for cfg, N, Ns, W, M, cache in [("C5", 5000, 1000, 4, 1, -1), ("C5", 5000, 1000,
     assert bool((t == ref).all())
     chk = h.selfcheck()                      # collective: residual of the solve and of the sharded factor, on the device
     assert chk["factor_residual"] < 1e-12 and chk["solve_residual"] < 1e-7, (cfg, chk)
+# LML gradient on the sharded handle (replicated L^-T solve, row groups of Ky^-1 and of the gradient tiles dealt out over the
+# ranks, one all-reduce) vs the dense oracle gradient; identical bits on every rank
+from thesis_code_b200 import _gpx
+for cfg, N, W in [("C2", 1100, 1), ("C3", 2500, 3), ("C4", 1500, 2)]:
+    c = synthetic.make_config(cfg, N=N, Ns=10)
+    kw = c["model"]["kwargs"]; kk = kw["kernel"]["kwargs"]
+    m = GPModel.from_config(kw); m.device = lr; m.distributed = True
+    h = m._get_handle(); h.set_option("outer_tiles", W)
+    m.init(c["X"], c["Y"])
+    nl = m.kernel.lengthscale.size
+    g = h.lml_grad(nl)
+    go = o.lml_grad(o.fit(c["X"], c["Y"], kw["kernel"]["name"], float(m.kernel.variance[0]), m.kernel.lengthscale, m.kernel.ARD, kw["noise_prior"]))
+    assert nrm(g, go) < 1e-8, (cfg, g, go)
+    t = torch.from_numpy(g.copy()).cuda(); ref = t.clone(); dist.broadcast(ref, src=0)
+    assert bool((t == ref).all())
+# ... without a full replica of the factor it refuses on every rank instead of hanging
+h.set_option("cache_mb", 0); m.init(c["X"], c["Y"])
+try:
+    h.lml_grad(nl); raise SystemExit("gradient without a replica did not fail")
+except _gpx.GpxError as e:
+    assert "whole factor resident" in str(e), e
+# do_optimize on a sharded model: same optimum as the single-GPU run from the same start, identical parameters on the ranks
+c = synthetic.make_config("C2", N=700, Ns=50)
+kw = dict(c["model"]["kwargs"], do_optimize=True, noise_prior=None)
+res = []
+for shard in (False, True):
+    m = GPModel.from_config(kw); m.device = lr; m.distributed = shard
+    m.randomize_before_optimize = False; m.max_iters = 25
+    m.init(c["X"], c["Y"])
+    res.append((m._param_array().copy(), m.get_marginal_log_likelihood()))
+assert abs(res[0][1] - res[1][1]) / abs(res[0][1]) < 1e-5 and nrm(res[1][0], res[0][0]) < 1e-2, res
+t = torch.from_numpy(res[1][0]).cuda(); ref = t.clone(); dist.broadcast(ref, src=0)
+assert bool((t == ref).all())
+m.randomize_before_optimize = True; m.max_iters = 5           # random restart point: drawn once, shared through sync_rng
+np.random.seed(7 + rank)
+m.init(c["X"], c["Y"])
+t = torch.from_numpy(m._param_array().copy()).cuda(); ref = t.clone(); dist.broadcast(ref, src=0)
+assert bool((t == ref).all())
 # a sharded fit is a collective over identical inputs: different data on the ranks must raise, not hang
 c = synthetic.make_config("C2", N=600, Ns=10)
 m = GPModel.from_config(c["model"]["kwargs"]); m.device = lr; m.distributed = True

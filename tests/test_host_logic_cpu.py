@@ -165,9 +165,19 @@ def test_hyper_samples_keep_one_handle_each(fake):
     assert len(m._theta_handles) == 0
 
 
-def test_sharded_do_optimize_is_refused_with_an_explanation(fake, monkeypatch):
+def test_sharded_do_optimize_shares_its_random_draws_first(fake, monkeypatch):
+    """do_optimize on a sharded model (gpx_lml_grad works there when every rank holds the whole factor): before anything is
+    drawn from the global numpy RNG, the ranks agree on one seed (distributed.sync_rng); a torchrun sweep of independent
+    per-rank models (distributed = False) does not meet in that collective."""
+    from thesis_code_b200 import distributed as gdist
     monkeypatch.setenv("WORLD_SIZE", "2")
-    m = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True})
-    m.distributed = True
-    with pytest.raises(_gpx.GpxError, match="not available on a sharded handle"):
+    calls = []
+    monkeypatch.setattr(gdist, "sync_rng", lambda handle, dist=None: calls.append(handle) or 1)
+    monkeypatch.setattr(core_models.GPModel, "_optimize_hyperparameters", lambda self: calls.append("optimize"))
+    monkeypatch.setattr(core_models.GPModel, "_new_handle", lambda self, shard: FakeHandle())
+    for shard, expect in ((True, 2), (False, 1)):
+        calls.clear()
+        m = pkg.GPModel.from_config({"kernel": {"name": "GPyRBF"}, "do_optimize": True})
+        m.distributed = shard
         m.init(np.zeros((4, 1)), np.zeros((4, 1)))
+        assert len(calls) == expect and calls[-1] == "optimize", calls

@@ -348,8 +348,10 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                         raise NotImplementedError("noise_prior must be a number (fixed noise), None (free noise) or an object "
                                                   "with GPy's prior interface lnpdf / lnpdf_grad / rvs (see thesis_code_b200.priors)")
         if self.do_optimize and self._wants_sharding() and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            raise _gpx.GpxError("do_optimize / num_mcmc need gpx_lml_grad, which is not available on a sharded handle: "
-                                "optimise on one GPU (model.distributed = False), then refit sharded with do_optimize=False")
+            # sharded optimisation: gpx_lml_grad works on a sharded handle whose ranks hold the whole factor (it says so
+            # loudly otherwise); the ranks must draw the same random start point / momenta
+            from . import distributed as gdist
+            gdist.sync_rng(self._get_handle())
         if self.do_optimize and self.num_mcmc > 0:
             self._sample_hyperparameters()           # sets _current_thetas (one per retained HMC sample)
             return

@@ -1104,13 +1104,30 @@ int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double
 int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     if (!h) return -1;
     if (!h->fitted) return fail(h, -1, "gpx_lml_grad called before a successful gpx_fit");
-    if (h->world > 1) return fail(h, -6, "gpx_lml_grad: only available on a single-GPU handle (not built for the sharded factor yet)");
+    const int G = h->world;
+    // Sharded handle: every rank needs the whole factor (the panel cache of the fit holds it when memory allows -- the same
+    // replica the predict sweep uses); Y = L^-T is then solved redundantly on every rank (no exchange), the row groups of
+    // Ky^-1 = Y Y^T and of the gradient tiles are dealt out cyclically and the 2 + n_ls sums meet in one all-reduce.
+    if (G > 1 && h->cache_panels < h->npanels)
+        return fail(h, -6, "gpx_lml_grad on a sharded handle needs the whole factor resident on every rank, but the panel cache "
+                    "holds %d of %d panels (N too large for a replica, or cache_mb too small): optimise at a smaller N or on one GPU",
+                    h->cache_panels, h->npanels);
     const int nt = h->nt, n_ls = h->n_ls, nparam = n_ls + 3, stride = 2 + n_ls;
     if (!grad || capacity < nparam) return fail(h, -1, "gradient buffer too small: need %d", nparam);
     if (h->d > gpx_grad_max_d()) return fail(h, -1, "gpx_lml_grad supports input dimension <= %d", gpx_grad_max_d());
     GPX_CUDA(h, cudaSetDevice(h->device));
     // workspaces: Y = L^-T as an nt x nt tile matrix (in Tt), Ky^-1 packed lower, per-tile partial sums
     if (!h->finv_valid) { release(h, h->finv); release(h, h->finv_partial); h->finv_layout_cap = -1; }   // a stale latency-path inverse
+    int rc = 0;
+    DevBuf &kinv = h->g_kinv, &kinv_off = h->g_kinv_off, &partial = h->g_partial, &gout = h->g_out;   // kept between calls
+    auto cleanup = [&]() {};
+    // stage timing (GPX_GRAD_TRACE=1 prints it): development aid
+    static const bool trace = getenv("GPX_GRAD_TRACE") != nullptr;
+    cudaEvent_t tev[6] = {};
+    auto mark = [&](int i) { if (trace) { if (!tev[i]) cudaEventCreate(&tev[i]); cudaEventRecord(tev[i], h->st); } };
+    std::vector<int64_t> tc(nt), kc(nt);
+    int64_t o = 0;
+    for (int c = 0; c < nt; c++) { tc[c] = (int64_t)c * nt * GPX_TILE_ELEMS; kc[c] = o; o += (int64_t)(nt - c) * GPX_TILE_ELEMS; }
     {
         size_t fr = 0, tot = 0;
         GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
@@ -1123,21 +1140,23 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
             GPX_CUDA(h, cudaMemGetInfo(&fr, &tot));
             fr += h->Tt.bytes + h->g_kinv.bytes;
         }
-        if (need > 0.9 * (double)fr) return fail(h, -3, "gpx_lml_grad needs %.1f GB of workspace (N too large for one GPU)", need / 1e9);
+        if (need > 0.9 * (double)fr) rc = fail(h, -3, "gpx_lml_grad needs %.1f GB of workspace (N too large for one GPU)", need / 1e9);
     }
-    int rc;
-    DevBuf &kinv = h->g_kinv, &kinv_off = h->g_kinv_off, &partial = h->g_partial, &gout = h->g_out;   // kept between calls
-    auto cleanup = [&]() {};
-    // stage timing (GPX_GRAD_TRACE=1 prints it): development aid
-    static const bool trace = getenv("GPX_GRAD_TRACE") != nullptr;
-    cudaEvent_t tev[6] = {};
-    auto mark = [&](int i) { if (trace) { if (!tev[i]) cudaEventCreate(&tev[i]); cudaEventRecord(tev[i], h->st); } };
-    std::vector<int64_t> tc(nt), kc(nt);
-    int64_t o = 0;
-    for (int c = 0; c < nt; c++) { tc[c] = (int64_t)c * nt * GPX_TILE_ELEMS; kc[c] = o; o += (int64_t)(nt - c) * GPX_TILE_ELEMS; }
-    if ((rc = ensure(h, h->Tt, (size_t)nt * nt * GPX_TILE_BYTES)) || (rc = ensure(h, h->tt_coloff, (size_t)nt * 8)) ||
+    if (!rc) {
+        (rc = ensure(h, h->Tt, (size_t)nt * nt * GPX_TILE_BYTES)) || (rc = ensure(h, h->tt_coloff, (size_t)nt * 8)) ||
         (rc = ensure(h, kinv, (size_t)o * 8)) || (rc = ensure(h, kinv_off, (size_t)nt * 8)) ||
-        (rc = ensure(h, partial, (size_t)nt * nt * stride * 8)) || (rc = ensure(h, gout, (size_t)(stride + 1) * 8))) { cleanup(); return rc; }
+        (rc = ensure(h, partial, (size_t)nt * nt * stride * 8)) || (rc = ensure(h, gout, (size_t)(stride + 1) * 8));
+    }
+    if (G > 1) {   // every rank must take the same decision: a rank that bailed out alone would leave the others in the all-reduce
+        double ok = rc ? 0.0 : 1.0;
+        double* ds = ptr<double>(h->scal) + 5;
+        GPX_CUDA(h, cudaMemcpyAsync(ds, &ok, 8, cudaMemcpyHostToDevice, h->st));
+        GPX_NCCL(h, nccl().AllReduce(ds, ds, 1, ncclDouble, ncclMin, h->comm, h->st));
+        GPX_CUDA(h, cudaMemcpyAsync(&ok, ds, 8, cudaMemcpyDeviceToHost, h->st));
+        GPX_CUDA(h, cudaStreamSynchronize(h->st));
+        if (!rc && ok == 0.0) rc = fail(h, -3, "gpx_lml_grad: another rank ran out of workspace memory");
+    }
+    if (rc) { cleanup(); return rc; }
     cudaMemcpyAsync(h->tt_coloff.p, tc.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st);
     cudaMemcpyAsync(kinv_off.p, kc.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, h->st);
     cudaStreamSynchronize(h->st);
@@ -1148,11 +1167,12 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     gpx_launch_identity_tiles(Y, nt, h->st);
     h->launches++;
     mark(1);
-    for (int p = 0; p < h->npanels; p++) var_trsm_panel(h, Y, nt, lmat(h), p, true);
+    for (int p = 0; p < h->npanels; p++) var_trsm_panel(h, Y, nt, G > 1 ? panel_mat(h, p) : lmat(h), p, true);
     mark(2);
     // 2. Ky^-1 = Y Y^T (lower tiles; Y(I,K) = 0 for K < I, so the contraction starts at the row group's first tile)
-    const int RG = 8;
+    const int RG = G > 1 ? 4 : 8;
     for (int I0 = 0; I0 < nt; I0 += RG) {
+        if (G > 1 && (I0 / RG) % G != h->rank) continue;
         const int I1 = I0 + RG < nt ? I0 + RG : nt;
         GemmJob g{};
         g.A = Y; g.B = Y; g.C = Ki;
@@ -1164,8 +1184,9 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     // 3. dLML/dtheta = sum W .* dK/dtheta
     gpx_launch_lml_grad(Ki, nt, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, h->d, h->kernel_id, h->variance, h->rdiv,
                         ptr<double>(h->ls), n_ls, ptr<double>(h->alpha), h->O, h->Np, ptr<double>(partial),
-                        ptr<double>(gout), h->st);
+                        ptr<double>(gout), h->st, RG, G, h->rank);
     h->launches += 3;
+    if (G > 1) GPX_NCCL(h, nccl().AllReduce(gout.p, gout.p, (size_t)stride, ncclDouble, ncclSum, h->comm, h->st));
     mark(4);
     if (trace) {
         cudaStreamSynchronize(h->st);

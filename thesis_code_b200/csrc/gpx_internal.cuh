@@ -41,7 +41,7 @@ void gpx_launch_identity_block(TileMat T, int w, int j0, cudaStream_t st);      
 void gpx_launch_transpose_block(TileMat Y, TileMat M, int p0, int w, cudaStream_t st);  // M(p0+j, p0+k) = Y(k, p0+j)^T, k <= j < w
 void gpx_launch_lml_grad(TileMat Kinv, int nt, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
                          double variance, double rdiv, const double* ls, int n_ls, const double* alpha, int O, int64_t Np,
-                         double* partial, double* out, cudaStream_t st);
+                         double* partial, double* out, cudaStream_t st, int rg = 8, int world = 1, int rank = 0);
 
 
 struct DevBuf {

@@ -515,12 +515,14 @@ __global__ void __launch_bounds__(256) lml_grad_tile_kernel(TileMat Kinv, int nt
                                                             int kernel_id, double variance, double rdiv,
                                                             const double* __restrict__ ls, int n_ls,
                                                             const double* __restrict__ alpha, int O, int64_t Np,
-                                                            double* __restrict__ partial, int stride) {
+                                                            double* __restrict__ partial, int stride, int rg, int world,
+                                                            int rank) {
     extern __shared__ __align__(16) double sm[];
     const int I = blockIdx.x, J = blockIdx.y;
     const int tid = threadIdx.x;
     double* out = partial + ((int64_t)I * nt + J) * stride;
     if (I < J) return;
+    if (world > 1 && (I / rg) % world != rank) return;   // sharded handle: the row groups of Ky^-1 are dealt out cyclically
     const int dp = d | 1;
     double* sa = sm;
     double* sb = sa + GPX_TILE * dp;
@@ -686,12 +688,13 @@ void gpx_launch_identity_tiles(TileMat T, int nt, cudaStream_t st) {
 
 void gpx_launch_lml_grad(TileMat Kinv, int nt, const double* Xs, const double* xsq, int64_t N, int d, int kernel_id,
                          double variance, double rdiv, const double* ls, int n_ls, const double* alpha, int O, int64_t Np,
-                         double* partial, double* out, cudaStream_t st) {
+                         double* partial, double* out, cudaStream_t st, int rg, int world, int rank) {
     const int stride = 2 + n_ls;
     size_t smem = (size_t)(2 * GPX_TILE * (d | 1) + 2 * GPX_TILE + 8 * stride) * sizeof(double);
     dim3 grid(nt, nt);
+    if (world > 1) cudaMemsetAsync(partial, 0, (size_t)nt * nt * stride * sizeof(double), st);   // tiles of the other ranks
     lml_grad_tile_kernel<<<grid, 256, smem, st>>>(Kinv, nt, Xs, xsq, N, d, kernel_id, variance, rdiv, ls, n_ls, alpha, O, Np,
-                                                  partial, stride);
+                                                  partial, stride, rg, world, rank);
     lml_grad_reduce_kernel<<<stride, 256, 0, st>>>(partial, nt, stride, stride, out);
     // out[stride] = sum(alpha): gradient of the constant mean
     sum_kernel<<<1, 256, 0, st>>>(alpha, Np * O, out + stride);

@@ -102,3 +102,21 @@ def check_same_problem(handle, X, Y, theta, dist=None):
         raise GpxError("sharded GPModel: the ranks were given different data or hyper-parameters "
                        "(N, d, O, crc(X), crc(Y), crc(theta) max {} vs min {}); a sharded fit is a collective over "
                        "identical inputs -- use model.distributed = False for per-rank models".format(t[:fp.size], -t[fp.size:]))
+
+
+def sync_rng(handle, dist=None):
+    """Sharded ``do_optimize`` / HMC: every rank has to walk the same path (each objective evaluation is a collective fit
+    over identical hyper-parameters), but GPy's recipe draws its start point and its HMC momenta from the process-global
+    numpy RNG.  Rank 0 draws a seed from that RNG, it is broadcast, and every rank re-seeds ``np.random`` with it.
+    Returns the seed (None when not distributed)."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    device = torch.device("cuda", handle.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(np.random.randint(0, 2 ** 31 - 1))], dtype=torch.int64, device=device)
+    dist.broadcast(t, src=0)
+    seed = int(t.item())
+    np.random.seed(seed)
+    return seed
