@@ -821,22 +821,23 @@ int ensure_panel_inverse(gpx_t* h, int upto_panel) {
 
 // one panel step of the blocked variance solve  Tt <- Tt L^-T  for nb test tiles (rows of Tt), L operand = P
 // (upper_rows: Tt is known to be upper triangular in tile terms -- rows >= p1 are still zero -- so they are skipped)
-void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows) {
+void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows, int row0) {
     const int nt = h->nt, p0 = panel_begin(h, p), p1 = panel_end(h, p);
     const int nb = (upper_rows && p1 < nb_in) ? p1 : nb_in;
+    if (row0 >= nb) return;
     if (h->minv_active && !upper_rows) {
         GemmJob t{};   // Tt(:, panel) <- Tt(:, panel) M_p^T, in place, one tile row per CTA (see GemmJob::rowwise)
         t.A = Tt; t.B = TileMat{ptr<double>(h->minv), ptr<int64_t>(h->minv_coloff), 1}; t.C = Tt;
-        t.tri = 0; t.i0 = 0; t.i1 = nb; t.ncols = p1 - p0; t.jbase = p0; t.jW = GPX_JW_CONTIG; t.jstride = 0;
+        t.tri = 0; t.i0 = row0; t.i1 = nb; t.ncols = p1 - p0; t.jbase = p0; t.jW = GPX_JW_CONTIG; t.jstride = 0;
         t.k0 = p0; t.k1 = p1; t.bdiag = 0; t.overwrite = 1; t.rowwise = 1;
         gemm(h, t, h->st);
     } else {
-        trsm_inner_stepwise(h, Tt, nb, P, p0, p1);
+        trsm_inner_stepwise(h, Tt, nb, P, p0, p1, row0);
     }
     if (p1 < nt) {
         GemmJob u{};
         u.A = Tt; u.B = P; u.C = Tt;
-        u.tri = 0; u.i0 = 0; u.i1 = nb; u.ncols = nt - p1; u.jbase = p1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+        u.tri = 0; u.i0 = row0; u.i1 = nb; u.ncols = nt - p1; u.jbase = p1; u.jW = GPX_JW_CONTIG; u.jstride = 0;
         u.k0 = p0; u.k1 = p1; u.bdiag = 0; u.overwrite = 0;
         gemm(h, u, h->st);
     }
@@ -1106,8 +1107,9 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     if (!h->fitted) return fail(h, -1, "gpx_lml_grad called before a successful gpx_fit");
     const int G = h->world;
     // Sharded handle: every rank needs the whole factor (the panel cache of the fit holds it when memory allows -- the same
-    // replica the predict sweep uses); Y = L^-T is then solved redundantly on every rank (no exchange), the row groups of
-    // Ky^-1 = Y Y^T and of the gradient tiles are dealt out cyclically and the 2 + n_ls sums meet in one all-reduce.
+    // replica the predict sweep uses); the tile rows of Y = L^-T are then split over the ranks (each row is an independent
+    // solve against the replica) and exchanged, the row groups of Ky^-1 = Y Y^T and of the gradient tiles are dealt out
+    // cyclically and the 2 + n_ls sums meet in one all-reduce: 2 N^3 / (3 G) flop per rank + N^2 / 2 doubles exchanged.
     if (G > 1 && h->cache_panels < h->npanels)
         return fail(h, -6, "gpx_lml_grad on a sharded handle needs the whole factor resident on every rank, but the panel cache "
                     "holds %d of %d panels (N too large for a replica, or cache_mb too small): optimise at a smaller N or on one GPU",
@@ -1167,7 +1169,37 @@ int gpx_lml_grad(gpx_t* h, double* grad, int capacity) {
     gpx_launch_identity_tiles(Y, nt, h->st);
     h->launches++;
     mark(1);
-    for (int p = 0; p < h->npanels; p++) var_trsm_panel(h, Y, nt, G > 1 ? panel_mat(h, p) : lmat(h), p, true);
+    // Sharded: the tile rows of Y are independent (row i is e_i^T L^-T), so each rank solves one contiguous block of them --
+    // boundaries balance the work, ~ (nt - i)^2 per row -- against its replica of the factor, and the blocks are exchanged
+    // with in-place broadcasts (column by column: a block's rows of one tile column are contiguous).
+    std::vector<int> bnd(G + 1, nt);
+    bnd[0] = 0;
+    if (G > 1) {
+        double total = 0.0, cum = 0.0;
+        for (int i = 0; i < nt; i++) total += (double)(nt - i) * (nt - i) + 4.0 * nt;
+        int r = 1;
+        for (int i = 0; i < nt && r < G; i++) {
+            cum += (double)(nt - i) * (nt - i) + 4.0 * nt;
+            while (r < G && cum >= total * r / G) bnd[r++] = i + 1;
+        }
+    }
+    const int my0 = bnd[h->rank], my1 = bnd[h->rank + 1];
+    for (int p = 0; p < h->npanels; p++) {
+        if (G == 1) var_trsm_panel(h, Y, nt, lmat(h), p, true);
+        else if (my0 < my1) var_trsm_panel(h, Y, my1, panel_mat(h, p), p, true, my0);
+    }
+    if (G > 1) {
+        for (int r = 0; r < G; r++) {
+            const int a = bnd[r], b = bnd[r + 1];
+            if (a >= b) continue;
+            GPX_NCCL(h, nccl().GroupStart());
+            for (int c = (a / h->W) * h->W; c < nt; c++) {
+                double* blk = Y.base + tc[c] + (int64_t)a * GPX_TILE_ELEMS;
+                nccl().Broadcast(blk, blk, (size_t)(b - a) * GPX_TILE_ELEMS, ncclDouble, r, h->comm, h->st);
+            }
+            GPX_NCCL(h, nccl().GroupEnd());
+        }
+    }
     mark(2);
     // 2. Ky^-1 = Y Y^T (lower tiles; Y(I,K) = 0 for K < I, so the contraction starts at the row group's first tile)
     const int RG = G > 1 ? 4 : 8;

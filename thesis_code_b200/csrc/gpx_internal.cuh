@@ -364,7 +364,7 @@ inline int ensure_panel_events(gpx_t* h, int npanels) {
 }
 
 
-void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows = false);
+void var_trsm_panel(gpx_t* h, TileMat Tt, int nb_in, TileMat P, int p, bool upper_rows = false, int row0 = 0);
 int var_trsm(gpx_t* h, TileMat Tt, int nb);
 int backward_solve(gpx_t* h);
 int ensure_panel_inverse(gpx_t* h, int upto_panel);
