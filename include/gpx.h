@@ -137,6 +137,9 @@ GPX_API int gpx_predict_cov(gpx_t* h, const double* Xs, int64_t Ns, double* mean
  * (n_ls + 3 values; returns that count, or < 0).  Replaces the gradient GPy's optimize() evaluates each L-BFGS step when
  * GPModel is built with do_optimize=True (src/models/core_models.py:211-223): dL_dK = 0.5 (alpha alpha^T - O Ky^-1),
  * Ky^-1 from the tiled factor (L^-T by the DMMA triangular solve, then Y Y^T), reduced against dK/dtheta on the fly.
+ * The workspaces stay in the handle between calls (an optimiser calls this once per iteration).  On a sharded handle the
+ * call is a collective: it needs the whole factor resident on every rank (the panel cache of gpx_fit; -6 otherwise), splits
+ * the rows of L^-T and the row groups of Ky^-1 over the ranks and all-reduces the sums -- every rank gets identical bits.
  */
 GPX_API int gpx_lml_grad(gpx_t* h, double* grad, int capacity);
 
