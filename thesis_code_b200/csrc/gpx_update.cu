@@ -439,32 +439,42 @@ __global__ void __launch_bounds__(256) finv_gemv_kernel(TileMat Y, int C, int S,
         }
 }
 
-// var[s] = prior - sum_J | sum_c partial(J, c)[s] |^2 : one CTA per test row, fixed order (deterministic)
+// var[s] = prior - sum_J | sum_c partial(J, c)[s] |^2.  grid (nt, rows): CTA (J, s) finishes the 128 entries of v_J, squares
+// and sums them into colsq[s][J]; the CTA that arrives last (ticket counter, self-resetting) adds the nt column sums in a
+// fixed order -- deterministic, and no single CTA walks the whole partial-sum buffer (that took 52 us of a 370 us call).
 // (more than 4 right-hand sides are computed as two groups of 4: partial + group * gstride)
-__global__ void __launch_bounds__(1024) finv_var_kernel(const double* __restrict__ partial, int nt, int C, int S, int rhs,
-                                                        int64_t gstride, double prior, const double* __restrict__ ystats,
-                                                        int var_cols, double* __restrict__ var) {
-    __shared__ double red[32];
-    const int s = blockIdx.x, tid = threadIdx.x;
-    partial += (int64_t)(s / rhs) * gstride;
-    const int sl = s % rhs;
-    double a = 0.0;
-    for (int e = tid; e < nt * GPX_TILE; e += 1024) {
-        const int J = e >> 7, col = e & 127, nc = J / C + 1;
-        const double* p = partial + (((int64_t)J * S) * rhs + sl) * GPX_TILE + col;
-        double v = 0.0;
-        for (int c = 0; c < nc; c++) v += p[(int64_t)c * rhs * GPX_TILE];
-        a = fma(v, v, a);
-    }
+__global__ void __launch_bounds__(128) finv_var_kernel(const double* __restrict__ partial, int nt, int C, int S, int rhs,
+                                                       int64_t gstride, double prior, const double* __restrict__ ystats,
+                                                       int var_cols, double* __restrict__ colsq, int colsq_stride,
+                                                       unsigned int* __restrict__ tickets, double* __restrict__ var) {
+    __shared__ double red[4];
+    __shared__ bool last;
+    const int J = blockIdx.x, s = blockIdx.y, col = threadIdx.x, nc = J / C + 1;
+    const double* p = partial + (int64_t)(s / rhs) * gstride + (((int64_t)J * S) * rhs + (s % rhs)) * GPX_TILE + col;
+    double v = 0.0;
+    for (int c = 0; c < nc; c++) v += p[(int64_t)c * rhs * GPX_TILE];
+    double a = v * v;
     for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-    if ((tid & 31) == 0) red[tid >> 5] = a;
+    if ((col & 31) == 0) red[col >> 5] = a;
     __syncthreads();
-    if (tid < var_cols) {
+    if (col == 0) {
+        colsq[(int64_t)s * colsq_stride + J] = (red[0] + red[1]) + (red[2] + red[3]);
+        __threadfence();
+        last = atomicAdd(&tickets[s], 1u) == (unsigned)(nt - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (col < 32) {
         double t = 0.0;
-        for (int w = 0; w < 32; w++) t += red[w];
-        const double v = prior - t;
-        const double sd = ystats ? ystats[var_cols + tid] : 1.0;
-        var[(int64_t)s * var_cols + tid] = ystats ? v * (sd * sd) : v;
+        for (int j = col; j < nt; j += 32) t += __ldcg(&colsq[(int64_t)s * colsq_stride + j]);
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (col == 0) tickets[s] = 0u;
+        if (col < var_cols) {
+            const double x = prior - t;
+            const double sd = ystats ? ystats[var_cols + col] : 1.0;
+            var[(int64_t)s * var_cols + col] = ystats ? x * (sd * sd) : x;
+        }
     }
 }
 
@@ -502,6 +512,10 @@ __global__ void diag_identity_kernel(TileMat T) {
     gpx_publish_for_async_proxy();
 }
 
+// behind the partial sums in finv_partial: per-row column sums of squares [kVecRows][cap_nt] and the ticket counters
+inline size_t finv_partial_doubles(const gpx_t* h, int cap, int S) { return (size_t)cap * S * kVecRows * GPX_TILE; }
+inline double* finv_colsq(gpx_t* h) { return ptr<double>(h->finv_partial) + finv_partial_doubles(h, h->finv_layout_cap, h->finv_S); }
+inline unsigned int* finv_tickets(gpx_t* h) { return reinterpret_cast<unsigned int*>(finv_colsq(h) + (size_t)kVecRows * h->finv_layout_cap); }
 inline TileMat finvmat(gpx_t* h) { return TileMat{ptr<double>(h->finv), ptr<int64_t>(h->finv_coloff), 0}; }
 // right-hand sides per launch: 1, 2 or 4; 5..8 vectors run as two launches of 4 (the 8-wide instantiation needs 96 registers
 // and measured 3.5x slower per tile than the 4-wide one: too few loads in flight)
@@ -551,7 +565,7 @@ int build_factor_inverse(gpx_t* h) {
     int C = (int)((total + 8LL * h->num_sms - 1) / (8LL * h->num_sms));
     if (C < 1) C = 1;
     const int S = (cap - 1) / C + 1;
-    const size_t part_bytes = (size_t)cap * S * kVecRows * GPX_TILE * 8;
+    const size_t part_bytes = (finv_partial_doubles(h, cap, S) + (size_t)kVecRows * cap + 8) * 8;
     if (h->finv_layout_cap != cap || h->finv_layout_w != W || !h->finv.p) {
         release(h, h->finv); release(h, h->finv_partial);
         size_t fr = 0, tot = 0;
@@ -570,6 +584,7 @@ int build_factor_inverse(gpx_t* h) {
         h->finv_layout_cap = cap; h->finv_layout_w = W;
     }
     h->finv_C = C; h->finv_S = S;
+    GPX_CUDA(h, cudaMemsetAsync(finv_tickets(h), 0, 64, h->st));
     TileMat Y{ptr<double>(h->finv), ptr<int64_t>(h->finv_coloff), 0};
     GPX_CUDA(h, cudaMemsetAsync(h->finv.p, 0, (size_t)tiles * GPX_TILE_BYTES, h->st));
     diag_identity_kernel<<<nt, GPX_TILE, 0, h->st>>>(Y);
@@ -599,8 +614,9 @@ int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_c
         if (h->finv_valid) {   // explicit inverse: one triangular GEMV, no dependent chain
             const int rhs = finv_rhs(Ns);
             n += launch_finv_gemv(h, (int)Ns, w.b, st);
-            finv_var_kernel<<<(int)Ns, 1024, 0, st>>>(ptr<double>(h->finv_partial), nt, h->finv_C, h->finv_S, rhs, finv_gstride(h, rhs),
-                                                     prior, y_stats(h), var_cols, w.var); n++;
+            finv_var_kernel<<<dim3(nt, (int)Ns), 128, 0, st>>>(ptr<double>(h->finv_partial), nt, h->finv_C, h->finv_S, rhs,
+                                                              finv_gstride(h, rhs), prior, y_stats(h), var_cols, finv_colsq(h),
+                                                              h->cap_nt, finv_tickets(h), w.var); n++;
         } else {
             for (int J = 0; J < nt; J++) {
                 gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, w.b, w.z, Np, (int)Ns, 2 * h->num_sms, st); n++;
