@@ -164,7 +164,7 @@ struct gpx_handle {
     int64_t sp_key[3] = {-1, -1, -1};
     void* pin = nullptr;
     size_t pin_bytes = 0;
-    struct SmallGraph { uint64_t gen; int64_t Ns; int want_var, var_cols, include_noise, nodes; cudaGraphExec_t exec; };
+    struct SmallGraph { uint64_t gen; int64_t Ns; int want_var, var_cols, include_noise, nodes, hostio; cudaGraphExec_t exec; };
     std::vector<SmallGraph> graphs;
     // explicit inverse of the factor, Y = L^-T as a packed-upper tile matrix (column J holds the tile rows 0 .. end of J's
     // panel): the variance of <= 8 rows becomes ONE triangular GEMV over it instead of nt dependent substitution steps

@@ -383,8 +383,9 @@ int small_workspace(gpx_t* h) {
     if (h->pin_bytes < pin_bytes) {
         if (h->pin) cudaFreeHost(h->pin);
         h->pin = nullptr; h->pin_bytes = 0;
-        GPX_CUDA(h, cudaHostAlloc(&h->pin, pin_bytes, cudaHostAllocDefault));
+        GPX_CUDA(h, cudaHostAlloc(&h->pin, pin_bytes, cudaHostAllocMapped));   // the latency path's kernels read / write it in place
         h->pin_bytes = pin_bytes;
+        h->gen++;   // captured graphs point into the old buffer
     }
     return 0;
 }
@@ -600,15 +601,18 @@ int build_factor_inverse(gpx_t* h) {
 
 // the graph-capturable part of the latency path: loader -> K* (+ mean partials, + right-hand-side vectors) -> mean
 // -> [forward substitution -> variance].  Returns the number of kernels launched.
-int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_cols, int include_noise, cudaStream_t st) {
+// xin / mean_out / var_out: the workspace copies, or (host callers) the mapped pinned buffer itself -- the loader reads the
+// test rows and the reduce kernels write the results straight through it, which saves three cudaMemcpyAsync calls per predict.
+int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_cols, int include_noise, cudaStream_t st,
+                const double* xin, double* mean_out, double* var_out) {
     const int nt = h->nt, d = h->d, O = h->O;
     const int64_t Np = h->Np;
     int n = 0;
-    gpx_launch_prep_x(w.Xin, Ns, GPX_TILE, d, ptr<double>(h->ls), h->ard, x_shift(h), x_scale(h), w.Xt, w.xtsq, st); n++;
+    gpx_launch_prep_x(xin, Ns, GPX_TILE, d, ptr<double>(h->ls), h->ard, x_shift(h), x_scale(h), w.Xt, w.xtsq, st); n++;
     gpx_launch_kcross(TileMat{nullptr, nullptr, 0}, 1, 1, nt, w.Xt, w.xtsq, Ns, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, d,
                       h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), O, Np, w.mean_partial, st,
                       want_var ? w.b : nullptr, (int)Ns); n++;
-    gpx_launch_mean_reduce(w.mean_partial, 1, nt, O, h->mean_const, y_stats(h), w.mean, 0, Ns, st); n++;
+    gpx_launch_mean_reduce(w.mean_partial, 1, nt, O, h->mean_const, y_stats(h), mean_out, 0, Ns, st); n++;
     if (want_var) {
         const double prior = h->variance + (include_noise ? h->noise : 0.0);
         if (h->finv_valid) {   // explicit inverse: one triangular GEMV, no dependent chain
@@ -616,12 +620,12 @@ int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_c
             n += launch_finv_gemv(h, (int)Ns, w.b, st);
             finv_var_kernel<<<dim3(nt, (int)Ns), 128, 0, st>>>(ptr<double>(h->finv_partial), nt, h->finv_C, h->finv_S, rhs,
                                                               finv_gstride(h, rhs), prior, y_stats(h), var_cols, finv_colsq(h),
-                                                              h->cap_nt, finv_tickets(h), w.var); n++;
+                                                              h->cap_nt, finv_tickets(h), var_out); n++;
         } else {
             for (int J = 0; J < nt; J++) {
                 gpx_launch_fwd_step(lmat(h), ptr<double>(h->linv), nt, J, w.b, w.z, Np, (int)Ns, 2 * h->num_sms, st); n++;
             }
-            vec_var_kernel<<<(int)Ns, 256, 0, st>>>(w.z, (int64_t)nt * GPX_TILE, Np, prior, y_stats(h), var_cols, w.var); n++;
+            vec_var_kernel<<<(int)Ns, 256, 0, st>>>(w.z, (int64_t)nt * GPX_TILE, Np, prior, y_stats(h), var_cols, var_out); n++;
         }
     }
     return n;
@@ -807,13 +811,18 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
     const SmallWs w = small_views(h);
     cudaStream_t st = h->st;
     double* pin = reinterpret_cast<double*>(h->pin);
+    const bool want_var = var != nullptr;
+    // host callers of the chain route: zero-copy through the mapped pinned buffer [X 128 d | mean 128 O | var 128 O]
+    const bool zc = mem == GPX_MEM_HOST && (!want_var || Ns <= kVecRows);
+    double *pin_mean = pin + GPX_TILE * d, *pin_var = pin_mean + GPX_TILE * O;
     if (mem == GPX_MEM_HOST) {
         memcpy(pin, Xs, (size_t)Ns * d * 8);
-        GPX_CUDA(h, cudaMemcpyAsync(w.Xin, pin, (size_t)Ns * d * 8, cudaMemcpyHostToDevice, st));
+        if (!zc) GPX_CUDA(h, cudaMemcpyAsync(w.Xin, pin, (size_t)Ns * d * 8, cudaMemcpyHostToDevice, st));
     } else {
         GPX_CUDA(h, cudaMemcpyAsync(w.Xin, Xs, (size_t)Ns * d * 8, cudaMemcpyDeviceToDevice, st));
     }
-    const bool want_var = var != nullptr;
+    const double* xin = zc ? pin : w.Xin;
+    double *mean_out = zc ? pin_mean : w.mean, *var_out = zc ? pin_var : w.var;
     if (want_var && Ns <= kVecRows && !h->finv_valid && !h->finv_failed && h->latency_inverse != 0) {
         // the acquisition / IPOPT loops predict one row at a time, thousands of times per fit: after a few such calls (or at
         // the first with latency_inverse = 1) pay N^3/3 flop once for the explicit inverse of the factor
@@ -827,7 +836,8 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
             // replay (or capture once per fit generation and shape) the whole launch chain as one CUDA graph
             gpx_handle::SmallGraph* g = nullptr;
             for (auto& e : h->graphs)
-                if (e.gen == h->gen && e.Ns == Ns && e.want_var == (int)want_var && e.var_cols == var_cols && e.include_noise == include_noise) g = &e;
+                if (e.gen == h->gen && e.Ns == Ns && e.want_var == (int)want_var && e.var_cols == var_cols && e.include_noise == include_noise &&
+                    e.hostio == (int)zc) g = &e;
             if (!g) {
                 for (auto it = h->graphs.begin(); it != h->graphs.end();) {   // drop stale generations, bound the cache
                     if (it->gen != h->gen || h->graphs.size() >= 8) { cudaGraphExecDestroy(it->exec); it = h->graphs.erase(it); }
@@ -835,11 +845,11 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
                 }
                 cudaGraph_t graph = nullptr;
                 GPX_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                const int nodes = small_chain(h, w, Ns, want_var, var_cols, include_noise, st);
+                const int nodes = small_chain(h, w, Ns, want_var, var_cols, include_noise, st, xin, mean_out, var_out);
                 cudaError_t ec = cudaStreamEndCapture(st, &graph);
                 if (ec != cudaSuccess || !graph) { cudaGetLastError(); return fail(h, -2, "CUDA graph capture of the predict chain failed: %s", cudaGetErrorString(ec)); }
                 gpx_handle::SmallGraph e{};
-                e.gen = h->gen; e.Ns = Ns; e.want_var = want_var; e.var_cols = var_cols; e.include_noise = include_noise; e.nodes = nodes;
+                e.gen = h->gen; e.Ns = Ns; e.want_var = want_var; e.var_cols = var_cols; e.include_noise = include_noise; e.nodes = nodes; e.hostio = zc;
                 ec = cudaGraphInstantiate(&e.exec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (ec != cudaSuccess) { cudaGetLastError(); return fail(h, -2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ec)); }
@@ -849,7 +859,7 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
             GPX_CUDA(h, cudaGraphLaunch(g->exec, st));
             h->launches += g->nodes;
         } else {
-            h->launches += small_chain(h, w, Ns, want_var, var_cols, include_noise, st);
+            h->launches += small_chain(h, w, Ns, want_var, var_cols, include_noise, st, xin, mean_out, var_out);
         }
     } else {
         // 9..128 rows with variance: one tile row through the blocked DMMA solve (workspace kept between calls)
@@ -864,9 +874,11 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
         if ((rc = var_reduce(h, Tt, 1, h->variance + (include_noise ? h->noise : 0.0), var_cols, w.var, 0, Ns))) return rc;
     }
     const size_t mb = (size_t)Ns * O * 8, vb = want_var ? (size_t)Ns * var_cols * 8 : 0;
-    if (mem == GPX_MEM_HOST) {
-        GPX_CUDA(h, cudaMemcpyAsync(pin, w.mean, mb, cudaMemcpyDeviceToHost, st));
-        if (want_var) GPX_CUDA(h, cudaMemcpyAsync(pin + GPX_TILE * O, w.var, vb, cudaMemcpyDeviceToHost, st));
+    if (zc) {
+        // results are already on their way into the pinned buffer
+    } else if (mem == GPX_MEM_HOST) {
+        GPX_CUDA(h, cudaMemcpyAsync(pin_mean, w.mean, mb, cudaMemcpyDeviceToHost, st));
+        if (want_var) GPX_CUDA(h, cudaMemcpyAsync(pin_var, w.var, vb, cudaMemcpyDeviceToHost, st));
     } else {
         GPX_CUDA(h, cudaMemcpyAsync(mean, w.mean, mb, cudaMemcpyDeviceToDevice, st));
         if (want_var) GPX_CUDA(h, cudaMemcpyAsync(var, w.var, vb, cudaMemcpyDeviceToDevice, st));
@@ -875,8 +887,8 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, -2, "CUDA error during predict (latency path): %s", cudaGetErrorString(e));
     if (mem == GPX_MEM_HOST) {
-        memcpy(mean, pin, mb);
-        if (want_var) memcpy(var, pin + GPX_TILE * O, vb);
+        memcpy(mean, pin_mean, mb);
+        if (want_var) memcpy(var, pin_var, vb);
     }
     gemm_collect(h);
     return 0;

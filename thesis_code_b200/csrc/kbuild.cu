@@ -18,7 +18,7 @@
 namespace {
 
 #ifndef GPX_KBUILD_MINBLOCKS
-#define GPX_KBUILD_MINBLOCKS 2
+#define GPX_KBUILD_MINBLOCKS 3
 #endif
 constexpr int kMaxD = 64;
 constexpr int kMaxFusedO = 4;   // outputs whose mean partial sums are fused into one K*-tile pass (more outputs: more passes)
