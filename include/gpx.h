@@ -190,7 +190,7 @@ GPX_API int64_t gpx_launch_count(const gpx_t* h);
  * full-width communicator at this percentage of the panels, default 72), "latency_inverse" (explicit inverse of the factor,
  * L^-T as a packed-upper tile matrix, for the latency path: the variance of <= 8 rows and the <= 8-point gpx_append become
  * triangular GEMV sweeps at HBM rate instead of nt dependent substitution steps; costs N^3/3 flop and the factor's memory
- * once per fit, appends inside the last tile keep it up to date.  -1 auto = built by the 16th small variance predict of a
+ * once per fit; appends keep it up to date (re-layouts of the storage drop it).  -1 auto = built by the 16th small variance predict of a
  * fit if it fits in 60 % of the free memory, 0 = never (drops a built one), 1 = at the first such predict). */
 GPX_API int gpx_set_option(gpx_t* h, const char* name, int64_t value);
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel of this handle is launched on, so that a caller can

@@ -587,7 +587,8 @@ def test_explicit_inverse_variance_route_matches_substitution_and_oracle(gpu_han
     """Variance of <= 8 rows through the explicit inverse of the factor (option latency_inverse; one triangular GEMV instead
     of nt dependent substitution steps): same numbers as the substitution route and the oracle for tile counts that are /
     are not multiples of the panel width, a single tile, reserve rows beyond N, several outputs with the output normaliser's
-    replicated variance columns; the automatic mode builds the inverse by the 16th call; appends and refits invalidate it."""
+    replicated variance columns; the automatic mode builds the inverse by the 16th call; appends keep it up to date (in-tile:
+    new columns; new tile rows: the last tile columns are recomputed), re-layouts and refits drop it."""
     h = gpu_handle
     h.set_option("predict_graph", graph)
     rng = np.random.RandomState(11)
@@ -634,6 +635,20 @@ def test_explicit_inverse_variance_route_matches_substitution_and_oracle(gpu_han
                 mean_b, var_b = h.predict(rng.rand(300, d), output_dim=O)                    # the factor itself got the rows too
                 chk = h.selfcheck()
                 assert chk["factor_residual"] < 1e-12 and chk["solve_residual"] < 1e-8, chk
+            if reserve:   # appends that open new tile rows (tile route) refresh only the inverse's last tile columns
+                for k in (130, 1, 100):
+                    Xn = rng.rand(k, d); Yn = np.stack([np.sin(3 * Xn.sum(1) + o_) for o_ in range(O)], 1)
+                    h.append(Xn, Yn)
+                    Xa, Ya = np.vstack([Xa, Xn]), np.vstack([Ya, Yn])
+                    sta = o.fit(Xa, Ya, name, 1.2, ls, ARD, 0.02, mean_const=0.1)
+                    assert abs(h.lml()[0] - sta["lml"]) / abs(sta["lml"]) < TOL
+                    before = h.launch_count()
+                    mean, var = h.predict(Xt[:3], output_dim=O)
+                    assert h.launch_count() - before == 5, (N, k)                             # still through the inverse
+                    om, ov = o.predict(sta, Xt[:3])
+                    assert normwise(mean, om) < TOL and normwise(var, ov[:, 0]) < TOL, (N, k)
+                    chk = h.selfcheck()
+                    assert chk["factor_residual"] < 1e-12 and chk["solve_residual"] < 1e-8, chk
             X, Y = Xa, Ya
             # without the inverse an append runs the substitution chain; in automatic mode the 16th small predict rebuilds it
             h.set_option("latency_inverse", 0); h.set_option("latency_inverse", -1)

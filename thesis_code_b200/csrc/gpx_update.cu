@@ -507,8 +507,8 @@ __global__ void finv_append_cols_kernel(TileMat Y, const double* __restrict__ U,
 }
 
 // diagonal tiles of a zeroed tile matrix <- I
-__global__ void diag_identity_kernel(TileMat T) {
-    double* tp = tile_ptr(T, blockIdx.x, blockIdx.x);
+__global__ void diag_identity_kernel(TileMat T, int j0) {
+    double* tp = tile_ptr(T, j0 + blockIdx.x, j0 + blockIdx.x);
     if (threadIdx.x < GPX_TILE) tp[gpx_tile_idx(threadIdx.x, threadIdx.x)] = 1.0;
     gpx_publish_for_async_proxy();
 }
@@ -588,7 +588,7 @@ int build_factor_inverse(gpx_t* h) {
     GPX_CUDA(h, cudaMemsetAsync(finv_tickets(h), 0, 64, h->st));
     TileMat Y{ptr<double>(h->finv), ptr<int64_t>(h->finv_coloff), 0};
     GPX_CUDA(h, cudaMemsetAsync(h->finv.p, 0, (size_t)tiles * GPX_TILE_BYTES, h->st));
-    diag_identity_kernel<<<nt, GPX_TILE, 0, h->st>>>(Y);
+    diag_identity_kernel<<<nt, GPX_TILE, 0, h->st>>>(Y, 0);
     h->launches++;
     const int keep = h->minv_active;
     h->minv_active = 0;
@@ -596,6 +596,36 @@ int build_factor_inverse(gpx_t* h) {
     h->minv_active = keep;
     h->finv_valid = true;
     h->gen++;   // captured predict graphs of this fit still run the substitution chain
+    return 0;
+}
+
+// gpx_append through the tile route (new tile rows from t0 on) with the inverse resident: the tile columns of Y = L^-T left
+// of t0's panel are unchanged (leading blocks of a triangular inverse), so only the columns [c0, nt) are recomputed --
+// zeroed, unit diagonal, the far updates of the earlier panels restricted to those columns, then the regular panel steps.
+// O(N^2 * new columns) like the append itself.
+int refresh_factor_inverse(gpx_t* h, int t0) {
+    const int W = h->W, nt = h->nt, cap = h->cap_nt, p0 = t0 / W, c0 = p0 * W;
+    TileMat Y = finvmat(h);
+    int64_t tiles = 0;
+    for (int c = 0; c < nt; c++) {
+        int p1 = (c / W + 1) * W;
+        if (p1 > cap) p1 = cap;
+        if (c >= c0) GPX_CUDA(h, cudaMemsetAsync(ptr<double>(h->finv) + tiles * GPX_TILE_ELEMS, 0, (size_t)p1 * GPX_TILE_BYTES, h->st));
+        tiles += p1;
+    }
+    diag_identity_kernel<<<nt - c0, GPX_TILE, 0, h->st>>>(Y, c0);
+    h->launches++;
+    const int keep = h->minv_active;
+    h->minv_active = 0;
+    for (int q = 0; q < p0; q++) {
+        GemmJob u{};
+        u.A = Y; u.B = lmat(h); u.C = Y;
+        u.tri = 0; u.i0 = 0; u.i1 = (q + 1) * W; u.ncols = nt - c0; u.jbase = c0; u.jW = GPX_JW_CONTIG; u.jstride = 0;
+        u.k0 = q * W; u.k1 = (q + 1) * W; u.bdiag = 0; u.overwrite = 0;
+        gemm(h, u, h->st);
+    }
+    for (int p = p0; p < h->npanels; p++) var_trsm_panel(h, Y, nt, lmat(h), p, true);
+    h->minv_active = keep;
     return 0;
 }
 
@@ -959,6 +989,7 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     h->launches++;
     h->N = N1; h->nt = nt1; h->npanels = (nt1 + W - 1) / W;
     h->gen++;
+    const bool had_finv = h->finv_valid && h->finv_layout_cap == h->cap_nt && h->finv_layout_w == W;   // (a re-layout dropped it)
     finv_invalidate(h);
     GPX_CUDA(h, cudaMemsetAsync(h->info.p, 0, 64, st));
     // 1. the new rows of Ky (tile rows t0 .. nt1-1; a partially filled tile row t0 is rebuilt whole)
@@ -1029,16 +1060,19 @@ int gpx_append(gpx_t* h, const double* Xn, int64_t k, const double* Yn, int mem)
     gpx_launch_lml(ptr<double>(h->linv), ptr<double>(h->alpha), ptr<double>(h->resid), (int64_t)nt1 * GPX_TILE, Np, O,
                    ptr<double>(h->scal), st);
     h->launches++;
+    // keep the explicit inverse of the factor (latency path) up to date: only its tile columns from t0's panel on change
+    if (!rc && had_finv && !(rc = refresh_factor_inverse(h, t0))) h->finv_valid = true;
     double hs[2] = {0, 0};
     int hinfo = 0;
     cudaMemcpyAsync(hs, h->scal.p, 16, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&hinfo, h->info.p, 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    if (rc) return rc;
+    if (rc) { finv_invalidate(h); return rc; }
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(h, -2, "CUDA error during append: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { finv_invalidate(h); return fail(h, -2, "CUDA error during append: %s", cudaGetErrorString(e)); }
     gemm_collect(h);
     if (hinfo != 0) {
+        finv_invalidate(h);
         fail(h, hinfo, "append: Ky is not positive definite: non-positive pivot at row %d", hinfo);
         return hinfo;
     }
