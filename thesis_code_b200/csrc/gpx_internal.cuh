@@ -26,6 +26,11 @@ void gpx_launch_mean_reduce(const double* mean_partial, int nbt, int nt, int O, 
 int gpx_var_reduce_splits(int nbt, int nt, int num_sms);
 void gpx_launch_var_reduce(TileMat Tt, int nbt, int nt, int S, double* partial, double prior_var, const double* ystats,
                            int var_cols, double* var, int64_t row0, int64_t Ns, cudaStream_t st);
+bool gpx_small_kstar_ok(int64_t ns, int d, int O);
+void gpx_launch_small_kstar(const double* Xin, int ns, int d, const double* ls, int ard, const double* shift, const double* scale,
+                            const double* Xs, const double* xsq, int64_t N, int nt, int kernel_id, double variance, double rdiv,
+                            const double* alpha, int O, int64_t Np, double mean_const, const double* ystats, double* vec_out,
+                            double* partial, unsigned int* ticket, double* mean, cudaStream_t st);
 void gpx_launch_detile(TileMat M, int lower, int64_t rows, int64_t cols, double* out, cudaStream_t st);
 void gpx_launch_fwd_step(TileMat L, const double* linv, int nt, int J, double* b, double* z, int64_t Np, int O,
                          int max_ctas, cudaStream_t st);

@@ -350,7 +350,8 @@ size_t moments_smem(int d) { return (size_t)(256 + d + 256 * d) * sizeof(double)
 // ---- host helpers --------------------------------------------------------------------------------------------------
 
 struct SmallWs {   // views into h->sp (one allocation, re-made when cap_nt / d / O change)
-    double *Xin, *Xt, *xtsq, *mean_partial, *b, *z, *mean, *var;
+    double *Xin, *Xt, *xtsq, *mean_partial, *b, *z, *mean, *var, *kpartial;
+    unsigned int* ticket;
 };
 constexpr int kFinvAutoCalls = 16;
 constexpr int kVecRows = 8;   // variance of <= 8 rows: GEMV-style substitution; above: one tile row through the DMMA solve
@@ -367,17 +368,20 @@ SmallWs small_views(gpx_t* h) {
     w.z = p; p += kVecRows * Np;
     w.mean = p; p += GPX_TILE * O;
     w.var = p; p += GPX_TILE * O;
+    w.kpartial = p; p += cap * 64;            // per-tile partial sums of the fused small-batch K* kernel
+    w.ticket = reinterpret_cast<unsigned int*>(p);
     return w;
 }
 
 int small_workspace(gpx_t* h) {
     const int64_t d = h->d, O = h->O, Np = h->Np, cap = h->cap_nt;
-    const size_t doubles = (size_t)(2 * GPX_TILE * d + GPX_TILE + cap * GPX_TILE * O + 2 * kVecRows * Np + 2 * GPX_TILE * O);
+    const size_t doubles = (size_t)(2 * GPX_TILE * d + GPX_TILE + cap * GPX_TILE * O + 2 * kVecRows * Np + 2 * GPX_TILE * O + cap * 64 + 8);
     if (h->sp.p && h->sp_key[0] == cap && h->sp_key[1] == d && h->sp_key[2] == O) return 0;
     release(h, h->sp);
     int rc = ensure(h, h->sp, doubles * 8);
     if (rc) return rc;
     h->sp_key[0] = cap; h->sp_key[1] = d; h->sp_key[2] = O;
+    GPX_CUDA(h, cudaMemsetAsync(small_views(h).ticket, 0, 64, h->st));
     h->gen++;   // captured graphs point into the old workspace
     const size_t pin_bytes = (size_t)(GPX_TILE * d + 2 * GPX_TILE * O) * 8;
     if (h->pin_bytes < pin_bytes) {
@@ -638,11 +642,17 @@ int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_c
     const int nt = h->nt, d = h->d, O = h->O;
     const int64_t Np = h->Np;
     int n = 0;
-    gpx_launch_prep_x(xin, Ns, GPX_TILE, d, ptr<double>(h->ls), h->ard, x_shift(h), x_scale(h), w.Xt, w.xtsq, st); n++;
-    gpx_launch_kcross(TileMat{nullptr, nullptr, 0}, 1, 1, nt, w.Xt, w.xtsq, Ns, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, d,
-                      h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), O, Np, w.mean_partial, st,
-                      want_var ? w.b : nullptr, (int)Ns); n++;
-    gpx_launch_mean_reduce(w.mean_partial, 1, nt, O, h->mean_const, y_stats(h), mean_out, 0, Ns, st); n++;
+    if (gpx_small_kstar_ok(Ns, d, O)) {   // <= 8 rows: loader + K* + mean in one kernel
+        gpx_launch_small_kstar(xin, (int)Ns, d, ptr<double>(h->ls), h->ard, x_shift(h), x_scale(h), ptr<double>(h->Xs),
+                               ptr<double>(h->xsq), h->N, nt, h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), O, Np,
+                               h->mean_const, y_stats(h), want_var ? w.b : nullptr, w.kpartial, w.ticket, mean_out, st); n++;
+    } else {
+        gpx_launch_prep_x(xin, Ns, GPX_TILE, d, ptr<double>(h->ls), h->ard, x_shift(h), x_scale(h), w.Xt, w.xtsq, st); n++;
+        gpx_launch_kcross(TileMat{nullptr, nullptr, 0}, 1, 1, nt, w.Xt, w.xtsq, Ns, ptr<double>(h->Xs), ptr<double>(h->xsq), h->N, d,
+                          h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), O, Np, w.mean_partial, st,
+                          want_var ? w.b : nullptr, (int)Ns); n++;
+        gpx_launch_mean_reduce(w.mean_partial, 1, nt, O, h->mean_const, y_stats(h), mean_out, 0, Ns, st); n++;
+    }
     if (want_var) {
         const double prior = h->variance + (include_noise ? h->noise : 0.0);
         if (h->finv_valid) {   // explicit inverse: one triangular GEMV, no dependent chain

@@ -378,6 +378,108 @@ static size_t kb_smem(int d) {
     return doubles * sizeof(double);
 }
 
+// ---- latency path, <= 8 test rows: loader + k(x*, X) + predictive mean in ONE kernel ----------------------------------------
+// The tile builder evaluates 128 x 128 entries per CTA whatever the number of valid test rows, and loader / K* / reduce are
+// three dependent launches; for the row-by-row callers (src/growth_model_GPR/ipopt_wrapper.py:55) this kernel does the same
+// arithmetic (prep_x's z-score / ARD scaling / numpy-order |x|^2, the Gram-trick r^2 with the same FMA chain, K_of_r) for just
+// the ns rows: grid nt CTAs x 128 threads, one training row per thread.  It writes k(x*_s, X) as right-hand-side vectors (for the
+// variance) and per-tile partial sums of k . alpha; the CTA that arrives last (self-resetting ticket) adds them in tile order.
+constexpr int kSmallRows = 8, kSmallMaxO = 8, kSmallMaxD = 256;
+template <int KID>
+__global__ void __launch_bounds__(128) small_kstar_kernel(const double* __restrict__ Xin, int ns, int d, const double* __restrict__ ls,
+                                                          int ard, const double* __restrict__ shift, const double* __restrict__ scale,
+                                                          const double* __restrict__ Xs, const double* __restrict__ xsq, int64_t N,
+                                                          double variance, double rdiv, const double* __restrict__ alpha, int O,
+                                                          int64_t Np, double mean_const, const double* __restrict__ ystats,
+                                                          double* __restrict__ vec_out, double* __restrict__ partial,
+                                                          unsigned int* __restrict__ ticket, double* __restrict__ mean) {
+    extern __shared__ __align__(16) double sm[];
+    double* xt = sm;                          // [ns][d]
+    double* xtsq = xt + kSmallRows * d;       // [8]
+    double* red = xtsq + kSmallRows;          // [4 warps][8 * 8]
+    __shared__ bool last;
+    const int J = blockIdx.x, nt = gridDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t i = (int64_t)J * GPX_TILE + tid;
+    for (int e = tid; e < ns * d; e += GPX_TILE) {
+        const int k = e % d;
+        double v = Xin[e];
+        if (shift) v = (v - shift[k]) / scale[k];
+        if (ard) v = v / ls[k];
+        xt[e] = v;
+    }
+    __syncthreads();
+    if (tid < ns) xtsq[tid] = gpx_numpy_sumsq(xt + tid * d, d);
+    __syncthreads();
+    double dot[kSmallRows];
+#pragma unroll
+    for (int q = 0; q < kSmallRows; q++) dot[q] = 0.0;
+    const double* xi = Xs + i * d;
+    for (int k = 0; k < d; k++) {
+        const double b = xi[k];
+#pragma unroll
+        for (int q = 0; q < kSmallRows; q++)
+            if (q < ns) dot[q] = fma(xt[q * d + k], b, dot[q]);
+    }
+    const double bsq = xsq[i];
+    double kv[kSmallRows];
+#pragma unroll
+    for (int q = 0; q < kSmallRows; q++) {
+        kv[q] = 0.0;
+        if (q < ns) {
+            const double r2 = fmax(-2.0 * dot[q] + (xtsq[q] + bsq), 0.0);
+            if (i < N) kv[q] = gpx_k_of_r_t<KID>(variance, gpx_scaled_r(r2, rdiv));
+            if (vec_out) vec_out[(int64_t)q * Np + i] = kv[q];
+        }
+    }
+    // per-tile partial sums of k . alpha: warp shuffle tree, then the four warps in order
+    for (int o = 0; o < O; o++) {
+        const double a = alpha[(int64_t)o * Np + i];
+#pragma unroll
+        for (int q = 0; q < kSmallRows; q++) {
+            if (q < ns) {
+                double v = kv[q] * a;
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) red[warp * 64 + q * kSmallMaxO + o] = v;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < ns * O) {
+        const int q = tid / O, o = tid - q * O, e = q * kSmallMaxO + o;
+        partial[(int64_t)J * 64 + e] = (red[e] + red[64 + e]) + (red[128 + e] + red[192 + e]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = atomicAdd(ticket, 1u) == (unsigned)(nt - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (tid < ns * O) {
+        const int q = tid / O, o = tid - q * O, e = q * kSmallMaxO + o;
+        double m = 0.0;
+        for (int j = 0; j < nt; j++) m += __ldcg(&partial[(int64_t)j * 64 + e]);
+        m += mean_const;
+        if (ystats) m = m * ystats[O + o] + ystats[o];
+        mean[q * O + o] = m;
+    }
+    if (tid == 0) *ticket = 0u;
+}
+
+bool gpx_small_kstar_ok(int64_t ns, int d, int O) { return ns >= 1 && ns <= kSmallRows && O <= kSmallMaxO && d <= kSmallMaxD; }
+// partial: nt * 64 doubles; ticket: one zero-initialised counter
+void gpx_launch_small_kstar(const double* Xin, int ns, int d, const double* ls, int ard, const double* shift, const double* scale,
+                            const double* Xs, const double* xsq, int64_t N, int nt, int kernel_id, double variance, double rdiv,
+                            const double* alpha, int O, int64_t Np, double mean_const, const double* ystats, double* vec_out,
+                            double* partial, unsigned int* ticket, double* mean, cudaStream_t st) {
+    const size_t smem = (size_t)(kSmallRows * d + kSmallRows + 4 * 64) * sizeof(double);
+    switch (kernel_id) {
+#define GPX_SMALLK(K) case K: small_kstar_kernel<K><<<nt, GPX_TILE, smem, st>>>(Xin, ns, d, ls, ard, shift, scale, Xs, xsq, N, variance, rdiv, \
+                                  alpha, O, Np, mean_const, ystats, vec_out, partial, ticket, mean); break;
+        GPX_SMALLK(0) GPX_SMALLK(1) GPX_SMALLK(2) GPX_SMALLK(3)
+#undef GPX_SMALLK
+    }
+}
+
 int gpx_kbuild_max_d() { return 1 << 20; }   // any input dimension (processed in chunks of kMaxD)
 int gpx_grad_max_d() { return kMaxD; }       // the gradient kernel keeps one partial sum per lengthscale in registers
 
