@@ -273,3 +273,43 @@ def test_large_golden_fixture_is_consistent(golden_large):
         assert g["var_with_noise"].min() > 0
     # C4's test draw does not depend on N: the stored test points are the first 512 of the config's own test set
     np.testing.assert_array_equal(golden_large["C4"]["Xs"], synthetic.make_config("C4", N=256, Ns=100000)["Xs"][:512])
+
+
+def test_explicit_inverse_identities_behind_the_latency_path():
+    """The algebra the latency path's explicit inverse Y = L^-T relies on (csrc/gpx_update.cu: finv_gemv_kernel, append_vec,
+    refresh_factor_inverse), checked in numpy against the oracle's own factorisation:
+      * var = prior - |Y^T k*|^2                                   (one triangular GEMV instead of a forward substitution)
+      * appending k rows:  Y_new = [[Y, -U C^-T], [0, C^-T]],  Z = Y^T K(X, X_new),  C = chol(K_nn + s^2 I - Z^T Z),  U = Y Z,
+        alpha_new = Y_new z_new with z_new = [z, C^-1 (r_new - Z^T z)]  (no backward substitution)
+      * the leading tile columns of Y do not change when rows are appended (only the new columns are recomputed)."""
+    import scipy.linalg as sla
+    rng = np.random.RandomState(3)
+    N, k, d = 300, 5, 3
+    X = rng.rand(N + k, d); Y = np.sin(3 * X.sum(1, keepdims=True)) + 0.05 * rng.randn(N + k, 1)
+    ls = np.array([0.4, 0.7, 1.1])
+    kw = dict(kernel="GPyMatern52", variance=1.3, lengthscale=ls, ARD=True, noise=0.02, mean_const=0.1)
+    st0 = o.fit(X[:N], Y[:N], **kw)
+    st1 = o.fit(X, Y, **kw)
+    L0, L1 = st0["L"], st1["L"]
+    Yinv = sla.solve_triangular(L0, np.eye(N), lower=True).T                    # Y = L^-T (upper triangular)
+    Xs = rng.rand(4, d)
+    Ks = o.kernel_matrix("GPyMatern52", X[:N], Xs, 1.3, ls, True)
+    mean, var = o.predict(st0, Xs)
+    v = Yinv.T @ Ks
+    assert np.allclose(1.3 + 0.02 - (v * v).sum(0), var[:, 0], rtol=1e-10, atol=0)
+    # append
+    Kn = o.kernel_matrix("GPyMatern52", X[:N], X[N:], 1.3, ls, True)
+    Z = Yinv.T @ Kn
+    S = o.kernel_matrix("GPyMatern52", X[N:], None, 1.3, ls, True) + (0.02 + st0["jitter"]) * np.eye(k) - Z.T @ Z
+    C = np.linalg.cholesky(S)
+    Cinv = sla.solve_triangular(C, np.eye(k), lower=True)
+    assert np.allclose(L1[N:, :N], Z.T, rtol=1e-9, atol=1e-12) and np.allclose(L1[N:, N:], C, rtol=1e-9, atol=1e-12)
+    U = Yinv @ Z
+    Ynew = np.block([[Yinv, -U @ Cinv.T], [np.zeros((k, N)), Cinv.T]])
+    Yref = sla.solve_triangular(L1, np.eye(N + k), lower=True).T
+    assert np.allclose(Ynew, Yref, rtol=1e-8, atol=1e-10)
+    assert np.array_equal(np.triu(Yref[:N, :N]) != 0, np.triu(Yinv) != 0) and np.allclose(Yref[:N, :N], Yinv, rtol=1e-9, atol=1e-12)
+    r = Y - 0.1
+    z = sla.solve_triangular(L0, r[:N], lower=True)
+    znew = np.vstack([z, Cinv @ (r[N:] - Z.T @ z)])
+    assert np.allclose(Ynew @ znew, st1["alpha"], rtol=1e-8, atol=1e-10)
