@@ -454,7 +454,13 @@ int gpx_set_option(gpx_t* h, const char* name, int64_t value) {
     if (!strcmp(name, "predict_graph")) { h->predict_graph = value ? 1 : 0; h->gen++; return 0; }
     if (!strcmp(name, "latency_inverse")) {   // -1 auto, 0 off (drops a built inverse), 1 build at the first small variance predict
         h->latency_inverse = (int)value;
-        if (value == 0 && h->finv_valid) { h->finv_valid = false; h->gen++; }
+        if (value == 0) {   // off: stop using a built inverse and give its memory back
+            if (h->finv_valid) { h->finv_valid = false; h->gen++; }
+            cudaSetDevice(h->device);
+            cudaStreamSynchronize(h->st);
+            release(h, h->finv); release(h, h->finv_partial);
+            h->finv_layout_cap = -1;
+        }
         h->finv_failed = false;
         return 0;
     }
