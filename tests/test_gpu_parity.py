@@ -422,7 +422,7 @@ def test_fused_normalizer_matches_reference_normalizer_fixtures(reference_pinned
     ref_cov = c["cov5"].reshape(5, 5) - float(c["noise"]) * ys2 + float(c["noise"]) * ys2 * np.eye(5)   # noise: everywhere -> diagonal
     assert cov5.shape == ((1, 5, 5, 1, 1) if ny else (1, 5, 5, 1))                # the reference's trailing-axis quirk
     assert normwise(cov5.reshape(5, 5), ref_cov) < TOL
-    assert normwise(m.get_mean(c["Xs"][:3]), mean[:, :3]) < 1e-13                # latency path (own summation order), same epilogue
+    assert normwise(m.get_mean(c["Xs"][:3]), mean[:, :3]) < 1e-11                # latency path (own summation order), same epilogue
     m.save(str(tmp_path / "nm"))
     m2 = NormalizerModel.load(str(tmp_path / "nm"))
     m2.model.jitter = 0.0
@@ -601,19 +601,23 @@ def test_explicit_inverse_variance_route_matches_substitution_and_oracle(gpu_han
             h.set_option("latency_inverse", 0)
             h.fit(X, Y, _gpx.KERNEL_IDS[name], 1.2, ls, 0.02, mean_const=0.1, ARD=ARD)
             st = o.fit(X, Y, name, 1.2, ls, ARD, 0.02, mean_const=0.1)
-            Xt = rng.rand(8, d)
+            Xt = rng.rand(64, d)
             nt = (N + 127) // 128
-            sub = {Ns: h.predict(Xt[:Ns], output_dim=O) for Ns in (1, 2, 3, 4, 5, 8)}
+            rows = (1, 2, 3, 4, 5, 8, 9, 31, 64)      # 9 .. 64 rows: groups of 8 through the inverse (else the tile route)
+            sub = {Ns: h.predict(Xt[:Ns], output_dim=O) for Ns in rows}
             h.set_option("latency_inverse", 1)
-            for Ns in (1, 2, 3, 4, 5, 8):
+            chain = lambda ns: 3 if ns <= 4 else 4    # fused loader + K* + mean, GEMV pass(es), variance
+            for Ns in rows:
                 for rep in range(2):
                     before = h.launch_count()
                     mean, var = h.predict(Xt[:Ns], output_dim=O)
                     used = h.launch_count() - before
-                    assert rep == 0 and Ns == 1 or used == (3 if Ns <= 4 else 4), (N, Ns, rep, used)   # fused loader + K* + mean, GEMV(s), variance
+                    expect = sum(chain(min(8, Ns - r0)) for r0 in range(0, Ns, 8))
+                    assert rep == 0 and Ns == 1 or used == expect, (N, Ns, rep, used, expect)
                     om, ov = o.predict(st, Xt[:Ns])
                     assert normwise(mean, om) < TOL and normwise(var, ov[:, 0]) < TOL, (N, Ns, rep)
-                    assert np.array_equal(mean, sub[Ns][0]) and normwise(var, sub[Ns][1]) < 1e-10, (N, Ns, rep)
+                    assert normwise(mean, sub[Ns][0]) < 1e-11 and normwise(var, sub[Ns][1]) < 1e-10, (N, Ns, rep)   # summation order only
+                    assert Ns > 8 or np.array_equal(mean, sub[Ns][0])
             mv, vv = h.predict(Xt[:3], output_dim=O, var_cols=O)
             assert np.array_equal(np.asarray(vv).reshape(3, -1)[:, 0], h.predict(Xt[:3], output_dim=O)[1])
             # appends inside the last tile go through the inverse too and keep it up to date (new columns of L^-T; alpha from it)

@@ -354,6 +354,7 @@ struct SmallWs {   // views into h->sp (one allocation, re-made when cap_nt / d 
     unsigned int* ticket;
 };
 constexpr int kFinvAutoCalls = 16;
+constexpr int kInvRows = 64;  // with the explicit inverse resident, up to 64 rows go through it in groups of 8 (128 rows: the tile route wins)
 constexpr int kVecRows = 8;   // variance of <= 8 rows: GEMV-style substitution; above: one tile row through the DMMA solve
 
 SmallWs small_views(gpx_t* h) {
@@ -642,6 +643,15 @@ int small_chain(gpx_t* h, const SmallWs& w, int64_t Ns, bool want_var, int var_c
     const int nt = h->nt, d = h->d, O = h->O;
     const int64_t Np = h->Np;
     int n = 0;
+    if (want_var && Ns > kVecRows) {
+        // 9 .. kInvRows rows with the explicit inverse resident: groups of 8 rows, each its own fused K* + GEMV + variance chain
+        // (the workspaces are re-used group after group on the stream)
+        for (int64_t r0 = 0; r0 < Ns; r0 += kVecRows) {
+            const int64_t ns = Ns - r0 < kVecRows ? Ns - r0 : kVecRows;
+            n += small_chain(h, w, ns, true, var_cols, include_noise, st, xin + r0 * d, mean_out + r0 * O, var_out + r0 * var_cols);
+        }
+        return n;
+    }
     if (gpx_small_kstar_ok(Ns, d, O)) {   // <= 8 rows: loader + K* + mean in one kernel
         gpx_launch_small_kstar(xin, (int)Ns, d, ptr<double>(h->ls), h->ard, x_shift(h), x_scale(h), ptr<double>(h->Xs),
                                ptr<double>(h->xsq), h->N, nt, h->kernel_id, h->variance, h->rdiv, ptr<double>(h->alpha), O, Np,
@@ -853,17 +863,16 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
     double* pin = reinterpret_cast<double*>(h->pin);
     const bool want_var = var != nullptr;
     // host callers of the chain route: zero-copy through the mapped pinned buffer [X 128 d | mean 128 O | var 128 O]
-    const bool zc = mem == GPX_MEM_HOST && (!want_var || Ns <= kVecRows);
+    // variance routes: <= 8 rows GEMV-style (substitution chain or explicit inverse); 9 .. 64 rows through the explicit inverse
+    // when it is resident; otherwise one tile row through the blocked DMMA solve
+    auto chain_route = [&]() { return !want_var || Ns <= kVecRows || (h->finv_valid && Ns <= kInvRows); };
     double *pin_mean = pin + GPX_TILE * d, *pin_var = pin_mean + GPX_TILE * O;
     if (mem == GPX_MEM_HOST) {
-        memcpy(pin, Xs, (size_t)Ns * d * 8);
-        if (!zc) GPX_CUDA(h, cudaMemcpyAsync(w.Xin, pin, (size_t)Ns * d * 8, cudaMemcpyHostToDevice, st));
+        memcpy(pin, Xs, (size_t)Ns * d * 8);   // (copied on to the workspace below unless the kernels read it in place)
     } else {
         GPX_CUDA(h, cudaMemcpyAsync(w.Xin, Xs, (size_t)Ns * d * 8, cudaMemcpyDeviceToDevice, st));
     }
-    const double* xin = zc ? pin : w.Xin;
-    double *mean_out = zc ? pin_mean : w.mean, *var_out = zc ? pin_var : w.var;
-    if (want_var && Ns <= kVecRows && !h->finv_valid && !h->finv_failed && h->latency_inverse != 0) {
+    if (want_var && Ns <= kInvRows && !h->finv_valid && !h->finv_failed && h->latency_inverse != 0) {
         // the acquisition / IPOPT loops predict one row at a time, thousands of times per fit: after a few such calls (or at
         // the first with latency_inverse = 1) pay N^3/3 flop once for the explicit inverse of the factor
         h->finv_calls++;
@@ -871,7 +880,11 @@ int gpx_predict_small(gpx_t* h, const double* Xs, int64_t Ns, double* mean, doub
             if ((rc = build_factor_inverse(h))) return rc;
         }
     }
-    if (!want_var || Ns <= kVecRows) {
+    const bool zc = mem == GPX_MEM_HOST && chain_route();
+    if (mem == GPX_MEM_HOST && !zc) GPX_CUDA(h, cudaMemcpyAsync(w.Xin, pin, (size_t)Ns * d * 8, cudaMemcpyHostToDevice, st));
+    const double* xin = zc ? pin : w.Xin;
+    double *mean_out = zc ? pin_mean : w.mean, *var_out = zc ? pin_var : w.var;
+    if (chain_route()) {
         if (h->predict_graph) {
             // replay (or capture once per fit generation and shape) the whole launch chain as one CUDA graph
             gpx_handle::SmallGraph* g = nullptr;
