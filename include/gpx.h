@@ -123,7 +123,9 @@ GPX_API int gpx_lml(gpx_t* h, double* lml, double* logdet, double* quad);
  * src/acquisition_functions.py:38,79 predict one or a few rows at a time, by the million): persistent workspaces and a
  * pinned staging buffer (no allocation, no cudaMemGetInfo), the variance of <= 8 rows by GEMV-style forward
  * substitution (L is read once, no tensor-core tile work) or, once the explicit inverse of the factor exists (option
- * "latency_inverse"), by one triangular GEMV over it; the whole launch chain replayed as a CUDA graph.
+ * "latency_inverse"), by one triangular GEMV over it (then up to 64 rows go that way, in groups of 8); for <= 8 rows the
+ * loader, k(x*, X) and the mean are one kernel; host buffers are read / written in place through a mapped pinned buffer;
+ * the whole launch chain is replayed as a CUDA graph.
  */
 GPX_API int gpx_predict(gpx_t* h, const double* Xs, int64_t Ns, double* mean, double* var, int var_cols,
                 int include_noise, int mem);
