@@ -24,6 +24,15 @@
  *     triangular 128x128 tiles, factored in place), the inverted diagonal tiles, alpha, workspaces, streams
  *     and the NCCL communicator.
  *   - there is NO CPU fallback: every entry point that computes launches sm_100a kernels.
+ *
+ * Differences from the ABI sketched in SURVEY.md section 8(b) (a proposal: the reference has no FFI to mirror):
+ *   - no per-call cudaStream_t argument: a handle owns three streams (update / panel factorisation / communication) whose
+ *     interplay is the look-ahead, so a caller's stream is attached once with gpx_set_stream() and every call orders itself
+ *     after it on the device; buffers may be host or device memory (`mem`), so numpy callers need no torch at all;
+ *   - no `precision` argument: the path is fp64 only.  The optional fp32-with-jitter mode cannot meet its own 1e-4 tolerance on
+ *     the BASELINE configs (measured: DESIGN.md section 1, profiles/r02_fp32_probe.txt);
+ *   - gpx_export_factor is gpx_export (alpha and, for small N, the dense factor); gpx_create takes one device (one process
+ *     per GPU; the ranks are joined by gpx_comm_init).
  */
 #ifndef GPX_H_
 #define GPX_H_

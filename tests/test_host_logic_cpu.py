@@ -181,3 +181,14 @@ def test_sharded_do_optimize_shares_its_random_draws_first(fake, monkeypatch):
         m.distributed = shard
         m.init(np.zeros((4, 1)), np.zeros((4, 1)))
         assert len(calls) == expect and calls[-1] == "optimize", calls
+
+
+def test_latency_inverse_attribute_reaches_the_handle(fake):
+    """GPModel.latency_inverse (None = automatic) is handed to every handle the model creates as the gpx option of the same name."""
+    X = np.random.RandomState(2).rand(12, 2); Y = X[:, :1]
+    for setting, expect in ((None, []), (True, [1]), (False, [0])):
+        m = _model()
+        m.latency_inverse = setting
+        m.init(X, Y)
+        got = [c[2] for c in m._handle.calls if c[0] == "set_option" and c[1] == "latency_inverse"]
+        assert got == expect, (setting, got)

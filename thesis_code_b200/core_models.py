@@ -172,6 +172,9 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                                                  # only when the environment says GPX_DISTRIBUTED=1 (opt-in: ranks of a sweep
                                                  # that fit different models must not meet in a collective)
         self.incremental = True                  # add_observations appends to the resident factor when it can
+        self.latency_inverse = None              # explicit inverse of the factor for row-by-row predictions / appends (gpx option
+                                                 # "latency_inverse"): None = automatic (after 16 small predicts of a fit),
+                                                 # True = at the first one, False = never
         self.max_cached_thetas = 16              # HMC: factorisations kept resident, one handle per hyper-sample
         self._normalize_input = False            # fused NormalizerModel (set by NormalizerModel, normalizer.py)
         self._normalize_output = False
@@ -196,7 +199,7 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
 
     def __setstate__(self, state):
         self.__dict__.update(state)
-        for k, v in (("distributed", None), ("incremental", True), ("max_cached_thetas", 16), ("_normalize_input", False),
+        for k, v in (("distributed", None), ("incremental", True), ("latency_inverse", None), ("max_cached_thetas", 16), ("_normalize_input", False),
                      ("_normalize_output", False), ("_theta_handles", {})):
             self.__dict__.setdefault(k, v)
 
@@ -241,6 +244,8 @@ class GPModel(ConfigMixin, MarginalLogLikelihoodMixin, ProbModel):
                 from . import distributed as gdist
                 gdist.init_handle_comm(h, dist)
         h.set_normalizer(self._normalize_input, self._normalize_output)
+        if getattr(self, "latency_inverse", None) is not None:
+            h.set_option("latency_inverse", 1 if self.latency_inverse else 0)
         return h
 
     def _get_handle(self):
