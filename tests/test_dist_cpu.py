@@ -61,6 +61,18 @@ def test_receive_buffers_alternate_over_non_owned_panels():
                 last = idx
 
 
+@pytest.mark.parametrize("nt,world", [(157, 2), (313, 2), (313, 4), (782, 8), (9, 2), (3, 8), (1, 2)])
+def test_sharded_gradient_row_blocks_cover_and_balance(nt, world):
+    """gpx_lml_grad on a sharded handle: each rank solves one contiguous block of tile rows of L^-T; the blocks cover all
+    rows once and, for problems with enough rows, carry the same share of the ~(nt - i)^2 work."""
+    b = gd.inverse_row_blocks(nt, world)
+    assert b[0] == 0 and b[-1] == nt and len(b) == world + 1 and all(b[i] <= b[i + 1] for i in range(world))
+    if nt >= 16 * world:
+        cost = [sum((nt - i) ** 2 + 4.0 * nt for i in range(b[r], b[r + 1])) for r in range(world)]
+        assert max(cost) / min(cost) < 1.25, (b, cost)
+        assert b[1] - b[0] < b[-1] - b[-2]          # the early rows are the expensive ones: the first block is the shortest
+
+
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})

@@ -52,6 +52,24 @@ def recv_buffer_index(p, rank, world):
     return (p - owned_before) & 1
 
 
+def inverse_row_blocks(nt, world):
+    """Boundaries [b_0 = 0, ..., b_world = nt] of the contiguous tile-row blocks of L^-T that the ranks of a sharded
+    ``gpx_lml_grad`` solve (mirrors the split in csrc/gpx_api.cu): row i costs ~ (nt - i)^2 + 4 nt tile steps (its far
+    updates + in-panel work), the blocks balance that cost."""
+    bnd = [0] + [nt] * world
+    if world > 1:
+        w = [(nt - i) * (nt - i) + 4.0 * nt for i in range(nt)]
+        total, cum, r = sum(w), 0.0, 1
+        for i in range(nt):
+            if r >= world:
+                break
+            cum += w[i]
+            while r < world and cum >= total * r / world:
+                bnd[r] = i + 1
+                r += 1
+    return bnd
+
+
 def init_handle_comm(handle, dist, rank=None, world=None):
     """Create the NCCL communicator inside ``handle`` from a torch.distributed process group: rank 0 draws the NCCL
     unique id, it is broadcast as bytes through ``dist`` (works with gloo and nccl backends), every rank joins."""
